@@ -1,0 +1,667 @@
+// C ABI of libcammiq_gpu.so (include/cammiq_gpu.h): host index load/flatten, device context,
+// and the query entry points that stand in for FqReader::query64_p / query64mt_p /
+// query64_sc (query.cpp:458-1080).  No CPU fallback anywhere: without a CUDA device every
+// context / query call fails with CQ_ENODEV.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cammiq_gpu.h"
+#include "flat_index.hpp"
+#include "index_codec.hpp"
+#include "scan_kernels.cuh"
+
+using namespace cammiq;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+	g_err = msg;
+	return code;
+}
+
+#define CQ_CUDA(call)                                                                      \
+	do {                                                                                   \
+		cudaError_t e_ = (call);                                                           \
+		if (e_ != cudaSuccess)                                                             \
+			return fail(CQ_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+	} while (0)
+
+struct cq_index {
+	FlatIndex flat;
+};
+
+struct cq_ctx {
+	int device = 0;
+	int n_sms = 0;
+	cudaStream_t stream = NULL;
+	bool own_stream = false;
+	cudaEvent_t ev[6] = {NULL, NULL, NULL, NULL, NULL, NULL};
+	// resident index
+	bool has_index = false;
+	uint32_t h = 0, n_genomes = 0;
+	uint64_t n_leaves_u = 0, n_leaves_d = 0, table_mask = 0;
+	TableSlot *d_table = NULL;
+	uint32_t *d_nodes_u = NULL, *d_nodes_d = NULL, *d_leaf_u_ref = NULL;
+	uint2 *d_leaf_d_ref = NULL;
+	// accumulators
+	unsigned long long *d_counts = NULL; // 2*(G+1)+4
+	uint32_t *d_rcount_u = NULL, *d_rcount_d = NULL;
+	uint32_t *d_partials = NULL;
+	uint32_t *d_spill = NULL;
+	unsigned long long *d_probe_count = NULL;
+	int grid = 0;
+	bool smem_counters = true;
+	size_t smem_bytes = 0;
+	// staged reads
+	uint8_t *d_bases = NULL;
+	uint64_t *d_offsets = NULL;
+	uint8_t *d_lengths = NULL;
+	size_t cap_bases = 0, cap_reads_off = 0, cap_reads_len = 0;
+	uint64_t staged_reads = 0, staged_stride = 0, staged_bytes = 0;
+	bool staged_has_offsets = false;
+	uint32_t staged_wpr = 0;
+	uint64_t *d_packed = NULL;
+	uint8_t *d_len = NULL;
+	size_t cap_packed = 0, cap_len = 0;
+	// SC pair records (device, grows)
+	unsigned long long *d_pairs = NULL;
+	size_t cap_pairs = 0;
+	// per-read outputs (device, sized per call)
+	uint8_t *d_read_class = NULL;
+	uint32_t *d_read_rid_a = NULL, *d_read_rid_b = NULL, *d_nleaf_u = NULL, *d_nleaf_d = NULL,
+		*d_leaf_u = NULL, *d_leaf_d = NULL;
+	size_t cap_per_read = 0, cap_leaf_lists = 0;
+	uint32_t leaf_cap = 0;
+	bool want_per_read = false, want_sets = false;
+	cq_timing timing;
+};
+
+extern "C" const char *cq_last_error(void) { return g_err.c_str(); }
+extern "C" int cq_abi_version(void) { return CQ_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------- index
+
+extern "C" int cq_index_load(const char *path_u, const char *path_d, double load_factor, cq_index **out) {
+	if (path_u == NULL || path_d == NULL || out == NULL)
+		return fail(CQ_EINVAL, "cq_index_load: NULL argument.");
+	*out = NULL;
+	auto t0 = std::chrono::high_resolution_clock::now();
+	DecodedIndex u, d;
+	std::string err_u, err_d;
+	int rc_u = 0, rc_d = 0;
+	// two loader threads, one per index file, like FqReader::loadIdx_p (query.cpp:109-123)
+	std::thread tu([&]() { rc_u = decodeIndexFile(path_u, u, err_u); });
+	std::thread td([&]() { rc_d = decodeIndexFile(path_d, d, err_d); });
+	tu.join();
+	td.join();
+	if (rc_u != 0)
+		return fail(rc_u, err_u);
+	if (rc_d != 0)
+		return fail(rc_d, err_d);
+	double decode_ms = std::chrono::duration<double, std::milli>(
+		std::chrono::high_resolution_clock::now() - t0).count();
+	cq_index *idx = new (std::nothrow) cq_index();
+	if (idx == NULL)
+		return fail(CQ_ENOMEM, "cq_index_load: out of memory.");
+	std::string err;
+	int rc;
+	try {
+		rc = flattenIndices(u, d, load_factor, idx->flat, err);
+	} catch (const std::bad_alloc &) {
+		delete idx;
+		return fail(CQ_ENOMEM, "cq_index_load: out of memory while flattening.");
+	}
+	if (rc != 0) {
+		delete idx;
+		return fail(rc, err);
+	}
+	idx->flat.decode_ms = decode_ms;
+	*out = idx;
+	return CQ_OK;
+}
+
+extern "C" void cq_index_free(cq_index *idx) { delete idx; }
+
+extern "C" int cq_index_get_info(const cq_index *idx, cq_index_info *info) {
+	if (idx == NULL || info == NULL)
+		return fail(CQ_EINVAL, "cq_index_get_info: NULL argument.");
+	const FlatIndex &f = idx->flat;
+	memset(info, 0, sizeof(*info));
+	info->hash_len = f.hash_len;
+	info->n_leaves_u = f.u.numLeaves();
+	info->n_leaves_d = f.d.numLeaves();
+	info->n_buckets_u = f.u.bucket_key.size();
+	info->n_buckets_d = f.d.bucket_key.size();
+	info->n_keys = f.n_keys;
+	info->n_table_buckets = f.n_table_buckets;
+	info->n_nodes_u = f.u.numNodes();
+	info->n_nodes_d = f.d.numNodes();
+	info->max_ref_id = std::max(f.u.max_ref_id, f.d.max_ref_id);
+	info->device_bytes = f.deviceBytes();
+	info->decode_ms = f.decode_ms;
+	info->flatten_ms = f.flatten_ms;
+	return CQ_OK;
+}
+
+extern "C" int cq_index_leaves(const cq_index *idx, int table, cq_leaf_view *view) {
+	if (idx == NULL || view == NULL || (table != CQ_TABLE_U && table != CQ_TABLE_D))
+		return fail(CQ_EINVAL, "cq_index_leaves: bad argument.");
+	const DecodedIndex &x = table == CQ_TABLE_U ? idx->flat.u : idx->flat.d;
+	view->n = x.numLeaves();
+	view->ref_id1 = x.ref_id1.data();
+	view->ref_id2 = x.ref_id2.data();
+	view->ucount1 = x.ucount1.data();
+	view->ucount2 = x.ucount2.data();
+	view->depth = x.depth.data();
+	return CQ_OK;
+}
+
+extern "C" int cq_index_map_sp(const cq_index *idx, int table, uint32_t n_genomes, uint64_t *offsets,
+		uint64_t *ids, uint64_t *total) {
+	if (idx == NULL || offsets == NULL || (table != CQ_TABLE_U && table != CQ_TABLE_D))
+		return fail(CQ_EINVAL, "cq_index_map_sp: bad argument.");
+	const DecodedIndex &x = table == CQ_TABLE_U ? idx->flat.u : idx->flat.d;
+	const uint64_t n = x.numLeaves();
+	std::vector<uint64_t> cnt((size_t) n_genomes + 2, 0);
+	auto ok = [&](uint32_t r) { return r >= 1 && r <= n_genomes; };
+	for (uint64_t l = 0; l < n; l++) {
+		if (ok(x.ref_id1[l])) cnt[x.ref_id1[l]]++;
+		if (x.doubly_unique && ok(x.ref_id2[l])) cnt[x.ref_id2[l]]++;
+	}
+	uint64_t sum = 0;
+	for (uint32_t r = 0; r <= n_genomes; r++) {
+		offsets[r] = sum;
+		sum += cnt[r];
+	}
+	offsets[n_genomes + 1] = sum;
+	if (total) *total = sum;
+	if (ids != NULL) {
+		std::vector<uint64_t> fill((size_t) n_genomes + 2, 0);
+		for (uint64_t l = 0; l < n; l++) {
+			uint32_t a = x.ref_id1[l], b = x.ref_id2[l];
+			if (ok(a)) ids[offsets[a] + fill[a]++] = l;
+			if (x.doubly_unique && ok(b)) ids[offsets[b] + fill[b]++] = l;
+		}
+	}
+	return CQ_OK;
+}
+
+extern "C" int cq_index_find_host(const cq_index *idx, int table, uint64_t bucket, const uint8_t *cand,
+		size_t len, uint64_t *leaf) {
+	if (idx == NULL || leaf == NULL || (table != CQ_TABLE_U && table != CQ_TABLE_D) || (len > 0 && cand == NULL))
+		return fail(CQ_EINVAL, "cq_index_find_host: bad argument.");
+	*leaf = flatFind(idx->flat, table, bucket, cand, len);
+	return CQ_OK;
+}
+
+// ----------------------------------------------------------------------------- context
+
+static void freeDevice(cq_ctx *c) {
+	cudaFree(c->d_table); cudaFree(c->d_nodes_u); cudaFree(c->d_nodes_d);
+	cudaFree(c->d_leaf_u_ref); cudaFree(c->d_leaf_d_ref); cudaFree(c->d_counts);
+	cudaFree(c->d_rcount_u); cudaFree(c->d_rcount_d); cudaFree(c->d_partials);
+	cudaFree(c->d_spill); cudaFree(c->d_probe_count);
+	c->d_table = NULL; c->d_nodes_u = c->d_nodes_d = c->d_leaf_u_ref = NULL; c->d_leaf_d_ref = NULL;
+	c->d_counts = NULL; c->d_rcount_u = c->d_rcount_d = c->d_partials = c->d_spill = NULL;
+	c->d_probe_count = NULL;
+	c->has_index = false;
+}
+
+extern "C" int cq_ctx_create(int device, void *stream, cq_ctx **out) {
+	if (out == NULL)
+		return fail(CQ_EINVAL, "cq_ctx_create: NULL argument.");
+	*out = NULL;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(CQ_ENODEV, std::string("no usable CUDA device (") +
+			(e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "); there is no CPU fallback.");
+	if (device < 0 || device >= n)
+		return fail(CQ_EINVAL, "cq_ctx_create: device ordinal out of range.");
+	CQ_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CQ_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(CQ_ENODEV, std::string("device ") + prop.name + " is not sm_100; this library is built for sm_100a only.");
+	cq_ctx *c = new (std::nothrow) cq_ctx();
+	if (c == NULL)
+		return fail(CQ_ENOMEM, "cq_ctx_create: out of memory.");
+	memset(&c->timing, 0, sizeof(c->timing));
+	c->device = device;
+	c->n_sms = prop.multiProcessorCount;
+	if (stream != NULL)
+		c->stream = (cudaStream_t) stream;
+	else {
+		cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+		if (e2 != cudaSuccess) {
+			delete c;
+			return fail(CQ_ECUDA, cudaGetErrorString(e2));
+		}
+		c->own_stream = true;
+	}
+	for (int i = 0; i < 6; i++)
+		cudaEventCreate(&c->ev[i]);
+	*out = c;
+	return CQ_OK;
+}
+
+extern "C" void cq_ctx_destroy(cq_ctx *c) {
+	if (c == NULL)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	freeDevice(c);
+	cudaFree(c->d_bases); cudaFree(c->d_offsets); cudaFree(c->d_lengths); cudaFree(c->d_packed);
+	cudaFree(c->d_len); cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
+	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
+	cudaFree(c->d_leaf_d);
+	for (int i = 0; i < 6; i++)
+		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->own_stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+template <typename T>
+static int uploadArray(T **dst, const T *src, size_t n, cudaStream_t st) {
+	size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+	CQ_CUDA(cudaMalloc((void **) dst, bytes));
+	if (n > 0)
+		CQ_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+	return CQ_OK;
+}
+
+extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genomes) {
+	if (c == NULL || idx == NULL || n_genomes == 0)
+		return fail(CQ_EINVAL, "cq_index_upload: bad argument.");
+	const FlatIndex &f = idx->flat;
+	if (std::max(f.u.max_ref_id, f.d.max_ref_id) > n_genomes)
+		return fail(CQ_EINVAL, "cq_index_upload: a leaf carries a genome id larger than n_genomes.");
+	for (size_t i = 0; i < f.u.ref_id1.size(); i++)
+		if (f.u.ref_id1[i] == 0)
+			return fail(CQ_EINVAL, "cq_index_upload: a unique leaf carries genome id 0.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	freeDevice(c);
+	int rc;
+	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), c->stream)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), c->stream)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), c->stream)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), c->stream)) != 0) return rc;
+	std::vector<uint2> dref(f.d.numLeaves());
+	for (size_t i = 0; i < dref.size(); i++)
+		dref[i] = make_uint2(f.d.ref_id1[i], f.d.ref_id2[i]);
+	if ((rc = uploadArray(&c->d_leaf_d_ref, dref.data(), dref.size(), c->stream)) != 0) return rc;
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+
+	c->h = f.hash_len;
+	c->n_genomes = n_genomes;
+	c->n_leaves_u = f.u.numLeaves();
+	c->n_leaves_d = f.d.numLeaves();
+	c->table_mask = f.n_table_buckets - 1;
+	const size_t ncnt = 2 * ((size_t) n_genomes + 1);
+	CQ_CUDA(cudaMalloc((void **) &c->d_counts, (ncnt + 4) * sizeof(unsigned long long)));
+	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u, std::max<size_t>(c->n_leaves_u, 1) * 4));
+	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d, std::max<size_t>(c->n_leaves_d, 1) * 4));
+	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, sizeof(unsigned long long)));
+
+	// launch geometry: persistent grid, a whole number of CTAs per SM
+	c->smem_counters = n_genomes <= kMaxSmemGenomes;
+	c->smem_bytes = c->smem_counters ? ncnt * sizeof(uint32_t) : 0;
+	if (c->smem_bytes > 48 * 1024) {
+		CQ_CUDA(cudaFuncSetAttribute(scan_reads_kernel<CQ_MODE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem_bytes));
+		CQ_CUDA(cudaFuncSetAttribute(scan_reads_kernel<CQ_MODE_SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem_bytes));
+	}
+	int per_sm = 0;
+	CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_reads_kernel<CQ_MODE_P>, kScanThreads, c->smem_bytes));
+	if (per_sm < 1)
+		return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
+	c->grid = per_sm * c->n_sms;
+	if (c->smem_counters)
+		CQ_CUDA(cudaMalloc((void **) &c->d_partials, (size_t) c->grid * ncnt * sizeof(uint32_t)));
+	CQ_CUDA(cudaMalloc((void **) &c->d_spill, (size_t) c->grid * kWarpsPerBlock * kSpillCap * sizeof(uint32_t)));
+	c->has_index = true;
+	return cq_reset(c);
+}
+
+extern "C" int cq_reset(cq_ctx *c) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_reset: no index resident.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
+	CQ_CUDA(cudaMemsetAsync(c->d_counts, 0, (ncnt + 4) * sizeof(unsigned long long), c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_rcount_u, 0, std::max<size_t>(c->n_leaves_u, 1) * 4, c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_rcount_d, 0, std::max<size_t>(c->n_leaves_d, 1) * 4, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	return CQ_OK;
+}
+
+template <typename T>
+static int ensure(T **ptr, size_t *cap, size_t need) {
+	if (need <= *cap && *ptr != NULL)
+		return CQ_OK;
+	if (*ptr) cudaFree(*ptr);
+	*ptr = NULL;
+	*cap = 0;
+	size_t n = std::max<size_t>(need, 1);
+	CQ_CUDA(cudaMalloc((void **) ptr, n * sizeof(T)));
+	*cap = n;
+	return CQ_OK;
+}
+
+// ------------------------------------------------------------------------------- query
+
+extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_reads_stage: no index resident.");
+	if (n_reads > 0 && (bases == NULL || lengths == NULL))
+		return fail(CQ_EINVAL, "cq_reads_stage: NULL read buffers.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	// extent of the base buffer and the longest read (sets the packed stride)
+	uint64_t total = 0;
+	uint32_t max_len = 1;
+	for (uint64_t i = 0; i < n_reads; i++) {
+		uint64_t end = (offsets ? offsets[i] : i * stride) + lengths[i];
+		total = std::max(total, end);
+		max_len = std::max<uint32_t>(max_len, lengths[i]);
+	}
+	int rc;
+	if ((rc = ensure(&c->d_bases, &c->cap_bases, total + 16)) != 0) return rc;
+	if ((rc = ensure(&c->d_lengths, &c->cap_reads_len, n_reads)) != 0) return rc;
+	if (offsets && (rc = ensure(&c->d_offsets, &c->cap_reads_off, n_reads)) != 0) return rc;
+	CQ_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	if (n_reads > 0) {
+		CQ_CUDA(cudaMemcpyAsync(c->d_bases, bases, total, cudaMemcpyHostToDevice, c->stream));
+		CQ_CUDA(cudaMemcpyAsync(c->d_lengths, lengths, n_reads, cudaMemcpyHostToDevice, c->stream));
+		if (offsets)
+			CQ_CUDA(cudaMemcpyAsync(c->d_offsets, offsets, n_reads * 8, cudaMemcpyHostToDevice, c->stream));
+	}
+	CQ_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	c->staged_reads = n_reads;
+	c->staged_stride = stride;
+	c->staged_has_offsets = offsets != NULL;
+	c->staged_bytes = total;
+	c->staged_wpr = (max_len + 31) / 32;
+	return CQ_OK;
+}
+
+extern "C" int cq_query_staged(cq_ctx *c, int mode) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_query_staged: no index resident.");
+	if (mode != CQ_MODE_P && mode != CQ_MODE_SC)
+		return fail(CQ_EINVAL, "cq_query_staged: bad mode.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	const uint64_t n = c->staged_reads;
+	const uint32_t wpr = std::max<uint32_t>(c->staged_wpr, 1);
+	int rc;
+	if ((rc = ensure(&c->d_packed, &c->cap_packed, (size_t) n * wpr + 1)) != 0) return rc;
+	if ((rc = ensure(&c->d_len, &c->cap_len, (size_t) n)) != 0) return rc;
+	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
+	if (mode == CQ_MODE_SC) {
+		// worst case every read adds a pair record on top of those already held
+		unsigned long long have = 0;
+		CQ_CUDA(cudaMemcpyAsync(&have, c->d_counts + ncnt + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+		CQ_CUDA(cudaStreamSynchronize(c->stream));
+		size_t need = (size_t) have + n;
+		if (need > c->cap_pairs) {
+			unsigned long long *np = NULL;
+			CQ_CUDA(cudaMalloc((void **) &np, std::max<size_t>(need, 1) * 8));
+			if (have > 0)
+				CQ_CUDA(cudaMemcpyAsync(np, c->d_pairs, have * 8, cudaMemcpyDeviceToDevice, c->stream));
+			CQ_CUDA(cudaStreamSynchronize(c->stream));
+			cudaFree(c->d_pairs);
+			c->d_pairs = np;
+			c->cap_pairs = need;
+		}
+	}
+	if (c->want_per_read) {
+		if ((rc = ensure(&c->d_read_class, &c->cap_per_read, (size_t) n)) != 0) return rc;
+		size_t cap2 = 0;
+		cap2 = 0; if ((rc = ensure(&c->d_read_rid_a, &cap2, (size_t) n)) != 0) return rc;
+		cap2 = 0; if ((rc = ensure(&c->d_read_rid_b, &cap2, (size_t) n)) != 0) return rc;
+	}
+	if (c->want_sets) {
+		size_t cap2 = 0;
+		cap2 = 0; if ((rc = ensure(&c->d_nleaf_u, &cap2, (size_t) n)) != 0) return rc;
+		cap2 = 0; if ((rc = ensure(&c->d_nleaf_d, &cap2, (size_t) n)) != 0) return rc;
+		cap2 = 0; if ((rc = ensure(&c->d_leaf_u, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
+		cap2 = 0; if ((rc = ensure(&c->d_leaf_d, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
+	}
+
+	CQ_CUDA(cudaEventRecord(c->ev[2], c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 8, c->stream));
+	if (n > 0) {
+		PackParams pp;
+		pp.bases = c->d_bases;
+		pp.offsets = c->staged_has_offsets ? c->d_offsets : NULL;
+		pp.stride = c->staged_stride;
+		pp.lengths = c->d_lengths;
+		pp.n_reads = n;
+		pp.words_per_read = wpr;
+		pp.h = c->h;
+		pp.packed = c->d_packed;
+		pp.len_out = c->d_len;
+		pp.n_invalid = c->d_counts + ncnt + 2;
+		uint64_t want_blocks = (n + 7) / 8;
+		int pgrid = (int) std::min<uint64_t>(want_blocks, (uint64_t) c->n_sms * 8);
+		pack_reads_kernel<<<pgrid, 256, 0, c->stream>>>(pp);
+		c->timing.kernel_launches++;
+	}
+	CQ_CUDA(cudaEventRecord(c->ev[3], c->stream));
+	if (n > 0) {
+		ScanParams sp;
+		memset(&sp, 0, sizeof(sp));
+		sp.table = c->d_table;
+		sp.table_mask = c->table_mask;
+		sp.nodes_u = c->d_nodes_u;
+		sp.nodes_d = c->d_nodes_d;
+		sp.leaf_u_ref = c->d_leaf_u_ref;
+		sp.leaf_d_ref = c->d_leaf_d_ref;
+		sp.h = c->h;
+		sp.n_genomes = c->n_genomes;
+		sp.packed = c->d_packed;
+		sp.len = c->d_len;
+		sp.words_per_read = wpr;
+		sp.n_reads = n;
+		sp.mode = mode;
+		sp.smem_counters = c->smem_counters ? 1 : 0;
+		sp.partials = c->d_partials;
+		sp.counts = c->d_counts;
+		sp.rcount_u = c->d_rcount_u;
+		sp.rcount_d = c->d_rcount_d;
+		sp.pair_records = c->d_pairs;
+		sp.spill = c->d_spill;
+		sp.probe_count = c->d_probe_count;
+		if (c->want_per_read) {
+			sp.read_class = c->d_read_class;
+			sp.read_rid_a = c->d_read_rid_a;
+			sp.read_rid_b = c->d_read_rid_b;
+		}
+		if (c->want_sets) {
+			sp.leaf_cap = c->leaf_cap;
+			sp.read_nleaf_u = c->d_nleaf_u;
+			sp.read_nleaf_d = c->d_nleaf_d;
+			sp.read_leaf_u = c->d_leaf_u;
+			sp.read_leaf_d = c->d_leaf_d;
+		}
+		if (mode == CQ_MODE_P)
+			scan_reads_kernel<CQ_MODE_P><<<c->grid, kScanThreads, c->smem_bytes, c->stream>>>(sp);
+		else
+			scan_reads_kernel<CQ_MODE_SC><<<c->grid, kScanThreads, c->smem_bytes, c->stream>>>(sp);
+		c->timing.kernel_launches++;
+		c->timing.scan_launches++;
+	}
+	CQ_CUDA(cudaEventRecord(c->ev[4], c->stream));
+	if (n > 0 && c->smem_counters) {
+		reduce_partials_kernel<<<(unsigned) ((ncnt + 255) / 256), 256, 0, c->stream>>>(
+			c->d_partials, (uint32_t) c->grid, (uint32_t) ncnt, c->d_counts);
+		c->timing.kernel_launches++;
+	}
+	CQ_CUDA(cudaEventRecord(c->ev[5], c->stream));
+	CQ_CUDA(cudaGetLastError());
+	return CQ_OK;
+}
+
+extern "C" int cq_sync(cq_ctx *c) {
+	if (c == NULL)
+		return fail(CQ_EINVAL, "cq_sync: NULL context.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	return CQ_OK;
+}
+
+extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
+	if (c == NULL || !c->has_index || out == NULL)
+		return fail(CQ_ESTATE, "cq_fetch: no index resident or NULL result.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	const size_t G1 = (size_t) c->n_genomes + 1, ncnt = 2 * G1;
+	std::vector<unsigned long long> counts(ncnt + 4);
+	CQ_CUDA(cudaMemcpyAsync(counts.data(), c->d_counts, (ncnt + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (out->rcount_u && mode == CQ_MODE_P && c->n_leaves_u)
+		CQ_CUDA(cudaMemcpyAsync(out->rcount_u, c->d_rcount_u, c->n_leaves_u * 4, cudaMemcpyDeviceToHost, c->stream));
+	if (out->rcount_d && mode == CQ_MODE_P && c->n_leaves_d)
+		CQ_CUDA(cudaMemcpyAsync(out->rcount_d, c->d_rcount_d, c->n_leaves_d * 4, cudaMemcpyDeviceToHost, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	if (out->cnt_u) memcpy(out->cnt_u, counts.data(), G1 * 8);
+	if (out->cnt_d) memcpy(out->cnt_d, counts.data() + G1, G1 * 8);
+	out->nundet = counts[ncnt];
+	out->nconf = counts[ncnt + 1];
+	out->n_invalid = counts[ncnt + 2];
+	out->n_pairs = 0;
+	if (mode == CQ_MODE_SC) {
+		// read_cnts_b (query.cpp:994-997): aggregate the per-read pair records on the host
+		uint64_t nrec = counts[ncnt + 3];
+		std::vector<unsigned long long> rec(nrec);
+		if (nrec > 0) {
+			CQ_CUDA(cudaMemcpy(rec.data(), c->d_pairs, nrec * 8, cudaMemcpyDeviceToHost));
+			std::sort(rec.begin(), rec.end());
+		}
+		uint64_t np = 0;
+		for (uint64_t i = 0; i < nrec;) {
+			uint64_t j = i;
+			while (j < nrec && rec[j] == rec[i]) j++;
+			if (out->pairs && np < out->pairs_cap) {
+				out->pairs[np].a = (uint32_t) (rec[i] >> 32);
+				out->pairs[np].b = (uint32_t) rec[i];
+				out->pairs[np].count = j - i;
+			}
+			np++;
+			i = j;
+		}
+		out->n_pairs = np;
+		if (out->pairs && np > out->pairs_cap)
+			return fail(CQ_EINVAL, "cq_fetch: pairs_cap too small for the pair map.");
+	}
+	return CQ_OK;
+}
+
+static int fetchPerRead(cq_ctx *c, uint64_t n, cq_result *out) {
+	if (c->want_per_read && n > 0) {
+		CQ_CUDA(cudaMemcpy(out->read_class, c->d_read_class, n, cudaMemcpyDeviceToHost));
+		CQ_CUDA(cudaMemcpy(out->read_rid_a, c->d_read_rid_a, n * 4, cudaMemcpyDeviceToHost));
+		CQ_CUDA(cudaMemcpy(out->read_rid_b, c->d_read_rid_b, n * 4, cudaMemcpyDeviceToHost));
+	}
+	if (c->want_sets && n > 0) {
+		const uint32_t cap = c->leaf_cap;
+		CQ_CUDA(cudaMemcpy(out->read_nleaf_u, c->d_nleaf_u, n * 4, cudaMemcpyDeviceToHost));
+		CQ_CUDA(cudaMemcpy(out->read_nleaf_d, c->d_nleaf_d, n * 4, cudaMemcpyDeviceToHost));
+		CQ_CUDA(cudaMemcpy(out->read_leaf_u, c->d_leaf_u, n * cap * 4, cudaMemcpyDeviceToHost));
+		CQ_CUDA(cudaMemcpy(out->read_leaf_d, c->d_leaf_d, n * cap * 4, cudaMemcpyDeviceToHost));
+		// the reference's std::set iterates in a fixed order; present the sets sorted
+		for (uint64_t r = 0; r < n; r++) {
+			uint32_t nu = std::min(out->read_nleaf_u[r], cap), nd = std::min(out->read_nleaf_d[r], cap);
+			std::sort(out->read_leaf_u + r * cap, out->read_leaf_u + r * cap + nu);
+			std::sort(out->read_leaf_d + r * cap, out->read_leaf_d + r * cap + nd);
+		}
+	}
+	return CQ_OK;
+}
+
+extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_query: no index resident (call cq_index_upload first).");
+	if (out == NULL)
+		return fail(CQ_EINVAL, "cq_query: NULL result.");
+	auto t0 = std::chrono::high_resolution_clock::now();
+	c->want_per_read = out->read_class != NULL && out->read_rid_a != NULL && out->read_rid_b != NULL;
+	c->want_sets = out->leaf_cap > 0 && out->read_nleaf_u && out->read_nleaf_d && out->read_leaf_u && out->read_leaf_d;
+	c->leaf_cap = c->want_sets ? out->leaf_cap : 0;
+	int rc = cq_reads_stage(c, bases, offsets, stride, lengths, n_reads);
+	if (rc == 0) rc = cq_query_staged(c, mode);
+	if (rc == 0) rc = cq_sync(c);
+	auto t1 = std::chrono::high_resolution_clock::now();
+	if (rc == 0) rc = cq_fetch(c, mode, out);
+	if (rc == 0) rc = fetchPerRead(c, n_reads, out);
+	c->want_per_read = c->want_sets = false;
+	c->leaf_cap = 0;
+	auto t2 = std::chrono::high_resolution_clock::now();
+	c->timing.d2h_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+	c->timing.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
+	return rc;
+}
+
+extern "C" int cq_get_device_counters(cq_ctx *c, cq_device_counters *out) {
+	if (c == NULL || !c->has_index || out == NULL)
+		return fail(CQ_ESTATE, "cq_get_device_counters: no index resident.");
+	out->d_counts = c->d_counts;
+	out->n_counts = 2 * ((uint64_t) c->n_genomes + 1) + 4;
+	out->d_rcount_u = c->d_rcount_u;
+	out->n_rcount_u = c->n_leaves_u;
+	out->d_rcount_d = c->d_rcount_d;
+	out->n_rcount_d = c->n_leaves_d;
+	return CQ_OK;
+}
+
+extern "C" int cq_get_timing(cq_ctx *c, cq_timing *out) {
+	if (c == NULL || out == NULL)
+		return fail(CQ_EINVAL, "cq_get_timing: NULL argument.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timing.h2d_ms = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timing.pack_ms = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->timing.scan_ms = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timing.reduce_ms = ms;
+	cudaGetLastError();
+	if (c->d_probe_count) {
+		unsigned long long pc = 0;
+		CQ_CUDA(cudaMemcpy(&pc, c->d_probe_count, 8, cudaMemcpyDeviceToHost));
+		c->timing.probes = pc;
+	}
+	*out = c->timing;
+	return CQ_OK;
+}
+
+extern "C" int cq_bench_random_sectors(cq_ctx *c, uint64_t n_probes, int iters, double *gsectors_per_s) {
+	if (c == NULL || !c->has_index || gsectors_per_s == NULL || iters < 1)
+		return fail(CQ_ESTATE, "cq_bench_random_sectors: bad argument or no index resident.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	unsigned long long *sink = c->d_probe_count;
+	cudaEvent_t a, b;
+	CQ_CUDA(cudaEventCreate(&a));
+	CQ_CUDA(cudaEventCreate(&b));
+	int grid = c->n_sms * 8;
+	random_sector_kernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->table_mask, n_probes, 12345, sink);
+	CQ_CUDA(cudaEventRecord(a, c->stream));
+	for (int i = 0; i < iters; i++)
+		random_sector_kernel<<<grid, 256, 0, c->stream>>>(c->d_table, c->table_mask, n_probes, 777 + 1000003ull * i, sink);
+	CQ_CUDA(cudaEventRecord(b, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	CQ_CUDA(cudaEventElapsedTime(&ms, a, b));
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	*gsectors_per_s = (double) n_probes * iters / (ms * 1e-3) * 1e-9;
+	c->timing.kernel_launches += iters + 1;
+	return CQ_OK;
+}

@@ -1,0 +1,122 @@
+#include "flat_index.hpp"
+
+#include <chrono>
+
+#include "../../include/cammiq_gpu.h"
+
+namespace cammiq {
+
+uint64_t FlatIndex::deviceBytes() const {
+	return table.size() * sizeof(TableSlot) + (u.nodes.size() + d.nodes.size()) * 4 +
+		u.numLeaves() * 4 + d.numLeaves() * 8 + (u.numLeaves() + d.numLeaves()) * 4;
+}
+
+namespace {
+
+// Insert (or find) key; returns the slot.  Linear probing by bucket.
+inline TableSlot *probeInsert(std::vector<TableSlot> &t, uint64_t mask, uint64_t key, bool &fresh) {
+	uint64_t b = mixKey(key) & mask;
+	for (;;) {
+		TableSlot *s = &t[b * kSlotsPerBucket];
+		for (int i = 0; i < kSlotsPerBucket; i++) {
+			if (s[i].key == key) {
+				fresh = false;
+				return &s[i];
+			}
+			if (s[i].key == kEmptyKey) {
+				s[i].key = key;
+				fresh = true;
+				return &s[i];
+			}
+		}
+		b = (b + 1) & mask;
+	}
+}
+
+} // namespace
+
+int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatIndex &out, std::string &err) {
+	auto t0 = std::chrono::high_resolution_clock::now();
+	if (u.doubly_unique || !d.doubly_unique) {
+		err = "Index flags: expected a unique (.bin1) and a doubly-unique (.bin2) index.";
+		return CQ_EFORMAT;
+	}
+	if (u.hash_len != d.hash_len) {
+		err = "Hash lengths of the unique and doubly-unique index differ.";
+		return CQ_EFORMAT;
+	}
+	if (load_factor <= 0.0 || load_factor > 1.0)
+		load_factor = 0.30;
+	out.hash_len = u.hash_len;
+	uint64_t upper = u.bucket_key.size() + d.bucket_key.size();
+	uint64_t want = (uint64_t) ((double) upper / (load_factor * kSlotsPerBucket)) + 1;
+	uint64_t nb = 64;
+	while (nb < want)
+		nb <<= 1;
+	out.n_table_buckets = nb;
+	TableSlot empty = {kEmptyKey, kRefNone, kRefNone};
+	out.table.assign(nb * kSlotsPerBucket, empty);
+	uint64_t mask = nb - 1, n_keys = 0;
+	const uint64_t key_limit = (u.hash_len >= 32) ? UINT64_MAX : (1ull << (2 * u.hash_len));
+	for (int t = 0; t < 2; t++) {
+		DecodedIndex &x = t == 0 ? u : d;
+		for (size_t i = 0; i < x.bucket_key.size(); i++) {
+			uint64_t key = x.bucket_key[i];
+			if (key >= key_limit) {
+				err = "Bucket key does not fit 2*hash_len bits.";
+				return CQ_EFORMAT;
+			}
+			bool fresh;
+			TableSlot *s = probeInsert(out.table, mask, key, fresh);
+			n_keys += fresh ? 1 : 0;
+			// a repeated key inside one file: the later bucket replaces the earlier one, as
+			// map64[bucket] = root does (hashtrie.cpp:500)
+			if (t == 0)
+				s->u_ref = x.bucket_root[i];
+			else
+				s->d_ref = x.bucket_root[i];
+		}
+	}
+	out.n_keys = n_keys;
+	out.u = std::move(u);
+	out.d = std::move(d);
+	out.flatten_ms = std::chrono::duration<double, std::milli>(
+		std::chrono::high_resolution_clock::now() - t0).count();
+	return CQ_OK;
+}
+
+uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t *cand, size_t len) {
+	uint64_t mask = fi.n_table_buckets - 1;
+	uint64_t b = mixKey(bucket) & mask;
+	uint32_t ref = kRefNone;
+	for (;;) {
+		const TableSlot *s = &fi.table[b * kSlotsPerBucket];
+		bool hit = false, has_empty = false;
+		for (int i = 0; i < kSlotsPerBucket; i++) {
+			if (s[i].key == bucket) {
+				ref = table == CQ_TABLE_U ? s[i].u_ref : s[i].d_ref;
+				hit = true;
+			}
+			if (s[i].key == kEmptyKey)
+				has_empty = true;
+		}
+		if (hit || has_empty)
+			break;
+		b = (b + 1) & mask;
+	}
+	const DecodedIndex &x = table == CQ_TABLE_U ? fi.u : fi.d;
+	size_t i = 0;
+	while (ref != kRefNone) {
+		if (refIsLeaf(ref))
+			return refLeafId(ref);
+		if (i >= len)
+			return UINT64_MAX;
+		int code = baseCode(cand[i++]);
+		if (code < 0)
+			return UINT64_MAX;
+		ref = x.nodes[4 * (size_t) refNodeId(ref) + code];
+	}
+	return UINT64_MAX;
+}
+
+} // namespace cammiq

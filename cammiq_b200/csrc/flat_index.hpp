@@ -1,0 +1,64 @@
+// Flattened, device-ready form of the two CAMMiQ indices.
+//
+//   prefix table   open addressing over 32-byte buckets (= one DRAM/L2 sector), two slots
+//                  per bucket: {key:u64, u_ref:u32, d_ref:u32}.  U and D share the hash
+//                  length (query.cpp:460), so ONE probe answers both tables.  Linear probing
+//                  by bucket; a lookup stops at the first bucket that holds the key or has a
+//                  free slot, so at the default load factor a miss costs one sector.
+//   trie nodes     per table, 4 child refs (16 bytes) per internal node; only buckets whose
+//                  root is not already a leaf have any (rare when h == k).
+//   leaf refs      per table, the genome id(s) the classification needs: u32 for U,
+//                  {u32,u32} for D.  The remaining leaf fields (ucount, depth) stay on the
+//                  host for the ILP set-up.
+#ifndef CAMMIQ_FLAT_INDEX_HPP
+#define CAMMIQ_FLAT_INDEX_HPP
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "index_codec.hpp"
+
+namespace cammiq {
+
+struct TableSlot {
+	uint64_t key;
+	uint32_t u_ref;
+	uint32_t d_ref;
+};
+static const uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+static const int kSlotsPerBucket = 2;
+
+// Bucket index of a key; the same function runs on the host (flatten, find_host) and in the
+// scan kernel.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint64_t mixKey(uint64_t x) {
+	x ^= x >> 31;
+	x *= 0x9E3779B97F4A7C15ull;
+	x ^= x >> 29;
+	x *= 0xBF58476D1CE4E5B9ull;
+	x ^= x >> 32;
+	return x;
+}
+
+struct FlatIndex {
+	uint32_t hash_len = 0;
+	uint64_t n_table_buckets = 0; // power of two
+	uint64_t n_keys = 0;
+	std::vector<TableSlot> table; // n_table_buckets * kSlotsPerBucket
+	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
+	double decode_ms = 0, flatten_ms = 0;
+
+	uint64_t deviceBytes() const;
+};
+
+// Build the merged prefix table from the two decoded indices (moved into out).
+int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatIndex &out, std::string &err);
+
+// Hash::find64_p on the flattened layout (host; layout verification only).
+uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t *cand, size_t len);
+
+} // namespace cammiq
+#endif

@@ -1,0 +1,54 @@
+// Host-side codec for CAMMiQ index files (index_u.bin1 / index_d.bin2 and their .aux).
+// Format: SURVEY.md section 5.9; reference reader binaryio.cpp:141-214, hashtrie.cpp:425-507,
+// reference writer binaryio.cpp:3-134, hashtrie.cpp:595-700.  Written from the format, not
+// from the reference code: iterative bit-stream decoder into flat arrays, no per-node heap
+// objects.
+#ifndef CAMMIQ_INDEX_CODEC_HPP
+#define CAMMIQ_INDEX_CODEC_HPP
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace cammiq {
+
+// Reference encoding shared by bucket roots and trie children.
+//   0                      no child / no trie
+//   0x80000000 | leaf_id   a leaf (file-order id)
+//   node_id + 1            an internal node; nodes[4*node_id + code] holds its children
+static const uint32_t kRefNone = 0u;
+static const uint32_t kRefLeafTag = 0x80000000u;
+inline bool refIsLeaf(uint32_t r) { return (r & kRefLeafTag) != 0; }
+inline uint32_t refLeafId(uint32_t r) { return r & ~kRefLeafTag; }
+inline uint32_t refNodeId(uint32_t r) { return r - 1; }
+
+struct DecodedIndex {
+	bool doubly_unique = false;
+	uint32_t hash_len = 0;
+	// buckets in file order
+	std::vector<uint64_t> bucket_key;
+	std::vector<uint32_t> bucket_root;
+	// internal trie nodes, 4 child refs each
+	std::vector<uint32_t> nodes;
+	// leaves in file order
+	std::vector<uint32_t> ref_id1, ref_id2;
+	std::vector<uint16_t> ucount1, ucount2;
+	std::vector<uint8_t> depth;
+	uint32_t max_ref_id = 0;
+
+	uint64_t numLeaves() const { return ref_id1.size(); }
+	uint64_t numNodes() const { return nodes.size() / 4; }
+};
+
+// Returns 0 or a CQ_E* code (include/cammiq_gpu.h); err receives a message.
+int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err);
+
+// Writer for the same format (tooling: synthetic indices, round-trip tests).
+// Buckets are emitted in the order given.
+int encodeIndexFile(const std::string &path, const DecodedIndex &idx, std::string &err);
+
+// 2-bit code of a base, -1 for anything outside ACGTacgt (query.cpp:1860-1883).
+int baseCode(uint8_t c);
+
+} // namespace cammiq
+#endif

@@ -1,0 +1,227 @@
+/*
+ * cammiq_gpu.h -- C ABI of libcammiq_gpu.so: the B200 (sm_100a) implementation of CAMMiQ's
+ * query-time read-matching path.  Plain C types only; every buffer in a signature is a
+ * caller-owned HOST buffer unless its name starts with d_ (device pointer).
+ *
+ * The reference has no FFI layer; the seam this ABI replaces is the body of three member
+ * functions of class FqReader plus the index load that feeds them (citations are
+ * /root/reference/src/<file>:<lines>):
+ *
+ *   cq_index_load / cq_index_free     Hash::loadIdx64_p + decodeTrie_p       hashtrie.cpp:425-507
+ *                                     FqReader::loadIdx_p (2 loader threads)  query.cpp:109-123
+ *   cq_index_leaves / cq_index_map_sp pleafNode fields, Hash::map_sp          hashtrie.hpp:37-47,60
+ *   cq_ctx_create / cq_ctx_destroy    FqReader ctor / dtor                    query.cpp:34-107
+ *   cq_index_upload                   end of loadIdx_p (index becomes resident)
+ *   cq_query                          FqReader::query64_p / query64mt_p (CQ_MODE_P)
+ *                                     FqReader::query64_sc (CQ_MODE_SC)       query.cpp:458-1080
+ *   cq_reset                          resetCounters / resetCounters_sc        query.cpp:1820-1858
+ *   cq_get_timing                     the "Time for query" bracket            query.cpp:645-647
+ *
+ * All functions return 0 on success and a negative CQ_E* code on failure;
+ * cq_last_error() then holds a message for the calling thread.  No exceptions cross the
+ * ABI.  There is NO CPU fallback: every cq_ctx_* / cq_query* call fails with CQ_ENODEV
+ * when no CUDA device is usable.
+ */
+#ifndef CAMMIQ_GPU_H
+#define CAMMIQ_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQ_ABI_VERSION 1
+
+enum {
+	CQ_OK = 0,
+	CQ_EINVAL = -1,  /* bad argument */
+	CQ_EIO = -2,     /* cannot open / read an index file */
+	CQ_EFORMAT = -3, /* index file violates the format */
+	CQ_ENOMEM = -4,
+	CQ_ENODEV = -5,  /* no usable CUDA device / library built without one */
+	CQ_ECUDA = -6,   /* CUDA runtime error, text in cq_last_error() */
+	CQ_ESTATE = -7   /* call order violated (e.g. query before upload) */
+};
+
+/* Which reference function cq_query stands in for. */
+enum {
+	CQ_MODE_P = 0, /* query64_p / query64mt_p: per-genome counts + per-leaf rcount */
+	CQ_MODE_SC = 1 /* query64_sc: per-genome counts + pair map read_cnts_b, no rcount */
+};
+
+enum { CQ_TABLE_U = 0, CQ_TABLE_D = 1 };
+
+/* Per-read decision (rows of the table in SURVEY.md section 8a; query.cpp:542-636, 977-1067). */
+enum {
+	CQ_CLASS_UNLABELED = 0, /* nundet++ */
+	CQ_CLASS_CONFLICT = 1,  /* nconf++ */
+	CQ_CLASS_U = 2,         /* cnt_u[rid_a]++ */
+	CQ_CLASS_D_PAIR = 3,    /* cnt_d[rid_a]++, cnt_d[rid_b]++ (SC: pairs[(rid_a,rid_b)]++) */
+	CQ_CLASS_UD = 4,        /* cnt_u[rid_a]++, cnt_d[rid_a]++ */
+	CQ_CLASS_D_INTER = 5    /* P: cnt_d[rid_a]++ ; SC: cnt_u[rid_a]++ and cnt_d[rid_a]++ */
+};
+
+typedef struct cq_index cq_index; /* host-side decoded + flattened index pair (U and D) */
+typedef struct cq_ctx cq_ctx;     /* one CUDA device: resident index, counters, streams */
+
+const char *cq_last_error(void);
+int cq_abi_version(void);
+
+/* ---------------------------------------------------------------- index (host side) -- */
+
+typedef struct {
+	uint32_t hash_len;       /* h, equal for both tables (assert at query.cpp:460) */
+	uint64_t n_leaves_u;     /* Hash::leaf_cnt of index_u.bin1 */
+	uint64_t n_leaves_d;     /* Hash::leaf_cnt of index_d.bin2 */
+	uint64_t n_buckets_u;    /* distinct h-mer buckets per table */
+	uint64_t n_buckets_d;
+	uint64_t n_keys;         /* distinct h-mers over both tables = occupied table slots */
+	uint64_t n_table_buckets;/* 32-byte buckets in the merged prefix table (power of two) */
+	uint64_t n_nodes_u;      /* CSR trie nodes below non-leaf bucket roots */
+	uint64_t n_nodes_d;
+	uint32_t max_ref_id;     /* largest genome id stored in a leaf */
+	uint64_t device_bytes;   /* bytes cq_index_upload will place on the device */
+	double decode_ms, flatten_ms;
+} cq_index_info;
+
+/*
+ * Decode <path_u>(+.aux) and <path_d>(+.aux) on two host threads and flatten them into the
+ * device layout.  load_factor in (0,1]: fraction of table slots occupied (0 = default).
+ * Fails with CQ_EFORMAT when the two hash lengths differ or a stream is malformed.
+ */
+int cq_index_load(const char *path_u, const char *path_d, double load_factor, cq_index **out);
+void cq_index_free(cq_index *idx);
+int cq_index_get_info(const cq_index *idx, cq_index_info *info);
+
+/* Leaf fields in FILE order (leaf id = order of appearance in the index file). */
+typedef struct {
+	uint64_t n;
+	const uint32_t *ref_id1;
+	const uint32_t *ref_id2; /* all zero for CQ_TABLE_U */
+	const uint16_t *ucount1;
+	const uint16_t *ucount2;
+	const uint8_t *depth;    /* hash_len + trie depth, uint8 arithmetic as in the reference */
+} cq_leaf_view;
+int cq_index_leaves(const cq_index *idx, int table, cq_leaf_view *view);
+
+/*
+ * Hash::map_sp as CSR: for rid in 1..n_genomes the file-order leaf ids that carry rid, in
+ * file order (D leaves appear under both ids).  offsets has n_genomes+2 entries; the ids
+ * of rid are ids[offsets[rid] .. offsets[rid+1]).  ids may be NULL to size the array;
+ * *total receives the entry count.
+ */
+int cq_index_map_sp(const cq_index *idx, int table, uint32_t n_genomes, uint64_t *offsets,
+		uint64_t *ids, uint64_t *total);
+
+/*
+ * Layout verification accessor (host): one Hash::find64_p on the FLATTENED layout.
+ * bucket = 2-bit hash of the h-mer, cand/len = the bases that follow it.  *leaf receives
+ * the file-order leaf id or UINT64_MAX.  Used by the flattening tests; it is not a query
+ * path and cq_query never calls it.
+ */
+int cq_index_find_host(const cq_index *idx, int table, uint64_t bucket, const uint8_t *cand,
+		size_t len, uint64_t *leaf);
+
+/* ------------------------------------------------------------------- device context -- */
+
+/* device = CUDA ordinal.  stream = a cudaStream_t the caller wants the work enqueued on
+   (e.g. torch's current stream), or NULL to let the context create its own. */
+int cq_ctx_create(int device, void *stream, cq_ctx **out);
+void cq_ctx_destroy(cq_ctx *ctx);
+
+/* Copy the flattened index to the device and size the counters for genome ids 1..n_genomes.
+   Fails with CQ_EINVAL when a leaf carries an id outside 1..n_genomes. */
+int cq_index_upload(cq_ctx *ctx, const cq_index *idx, uint32_t n_genomes);
+
+typedef struct {
+	uint32_t a, b; /* a <= b */
+	uint64_t count;
+} cq_pair_count;
+
+typedef struct {
+	/* in: capacities of the caller's buffers (0 / NULL = not wanted) */
+	uint64_t *cnt_u;        /* [n_genomes+1], index 0 unused: Genome::read_cnts_u */
+	uint64_t *cnt_d;        /* [n_genomes+1]: Genome::read_cnts_d */
+	uint32_t *rcount_u;     /* [n_leaves_u] pleafNode::rcount, file order (CQ_MODE_P) */
+	uint32_t *rcount_d;     /* [n_leaves_d] */
+	cq_pair_count *pairs;   /* [pairs_cap] read_cnts_b sorted by (a,b) (CQ_MODE_SC) */
+	uint64_t pairs_cap;
+	/* optional per-read records, [n_reads] each */
+	uint8_t *read_class;
+	uint32_t *read_rid_a;
+	uint32_t *read_rid_b;
+	/* optional per-read distinct leaf sets: up to leaf_cap file-order ids per table per read,
+	   ascending; read_nleaf_* hold the true set sizes */
+	uint32_t leaf_cap;
+	uint32_t *read_nleaf_u; /* [n_reads] */
+	uint32_t *read_nleaf_d;
+	uint32_t *read_leaf_u;  /* [n_reads * leaf_cap] */
+	uint32_t *read_leaf_d;
+	/* out */
+	uint64_t nundet;        /* FqReader::nundet */
+	uint64_t nconf;         /* FqReader::nconf */
+	uint64_t n_invalid;     /* reads the reference cannot process (see cq_query) */
+	uint64_t n_pairs;       /* distinct pairs (may exceed pairs_cap: then CQ_EINVAL) */
+} cq_result;
+
+/*
+ * One pass of the hot path over n_reads reads held in HOST memory as ASCII, exactly the
+ * state query64_* consumes: read i = bases[offsets[i] .. offsets[i]+lengths[i]).
+ * offsets may be NULL for fixed-stride storage: read i starts at i*stride.
+ * Synchronous.  Device counters ACCUMULATE across calls until cq_reset (the reference's
+ * counters live until resetCounters); on return `out` holds the accumulated totals.
+ * Per-read outputs cover this call's reads only.
+ *
+ * Defined behaviour where the reference has none: a read
+ * shorter than hash_len (query.cpp:486 underflows) or holding a byte outside ACGTacgt
+ * (symbolIdx = -1) is counted as unlabeled and in n_invalid.  'N' must already have been
+ * substituted by the FASTQ reader, as in the reference (query.cpp:383).
+ */
+int cq_query(cq_ctx *ctx, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out);
+
+/* Zero the accumulated counters (cnt_u/d, rcount, nundet, nconf, n_invalid, pairs). */
+int cq_reset(cq_ctx *ctx);
+
+/* ------------------------------------------- device-resident entry points (plumbing) -- */
+/*
+ * For callers that keep reads in HBM and combine counters themselves (bench.py, the
+ * multi-GPU launcher: one process per GPU, NCCL reduce of the counter block).
+ * cq_reads_stage copies ASCII reads host->device once; cq_query_staged runs pack + scan +
+ * count reduction on the staged reads asynchronously on the context's stream.
+ */
+int cq_reads_stage(cq_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads);
+int cq_query_staged(cq_ctx *ctx, int mode);
+int cq_sync(cq_ctx *ctx);
+/* Copy the accumulated totals to host buffers (same semantics as cq_query's out). */
+int cq_fetch(cq_ctx *ctx, int mode, cq_result *out);
+
+typedef struct {
+	void *d_counts;        /* uint64[2*(n_genomes+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid n_pair_records */
+	uint64_t n_counts;
+	void *d_rcount_u;      /* uint32[n_leaves_u] */
+	uint64_t n_rcount_u;
+	void *d_rcount_d;      /* uint32[n_leaves_d] */
+	uint64_t n_rcount_d;
+} cq_device_counters;
+int cq_get_device_counters(cq_ctx *ctx, cq_device_counters *out);
+
+typedef struct {
+	double h2d_ms, pack_ms, scan_ms, reduce_ms, d2h_ms, total_ms; /* last cq_query / cq_query_staged */
+	uint64_t scan_launches, kernel_launches;                      /* since ctx creation */
+	uint64_t probes;  /* prefix-table probes issued by the last scan (2*(rl-h+1) per valid read) */
+} cq_timing;
+int cq_get_timing(cq_ctx *ctx, cq_timing *out);
+
+/* Random 32-byte-sector gather micro-benchmark over the resident prefix table: the
+   measured "lookup roofline" of SURVEY.md section 8d.  n_probes random bucket reads;
+   *gsectors_per_s receives 1e-9 * sectors/s (CUDA-event timed). */
+int cq_bench_random_sectors(cq_ctx *ctx, uint64_t n_probes, int iters, double *gsectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
