@@ -435,6 +435,8 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		cap2 = 0; if ((rc = ensure(&c->d_nleaf_d, &cap2, (size_t) n)) != 0) return rc;
 		cap2 = 0; if ((rc = ensure(&c->d_leaf_u, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
 		cap2 = 0; if ((rc = ensure(&c->d_leaf_d, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
+		CQ_CUDA(cudaMemsetAsync(c->d_leaf_u, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
+		CQ_CUDA(cudaMemsetAsync(c->d_leaf_d, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 	}
 
 	CQ_CUDA(cudaEventRecord(c->ev[2], c->stream));
