@@ -68,7 +68,10 @@ class DeviceCounters(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("pack_ms", C.c_double), ("scan_ms", C.c_double),
                 ("reduce_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("scan_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("probes", C.c_uint64)]
+                ("scan_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("probes", C.c_uint64),
+                ("bucket_hits", C.c_uint64), ("leaf_hits", C.c_uint64), ("chained_loads", C.c_uint64),
+                ("pack_ms_sum", C.c_double), ("scan_ms_sum", C.c_double), ("reduce_ms_sum", C.c_double),
+                ("steps", C.c_uint64)]
 
 
 # every symbol include/cammiq_gpu.h declares: (restype, argtypes)
@@ -95,6 +98,7 @@ SYMBOLS = {
     "cq_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "cq_get_device_counters": (C.c_int, [C.c_void_p, C.POINTER(DeviceCounters)]),
     "cq_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "cq_timing_reset": (C.c_int, [C.c_void_p]),
     "cq_bench_random_sectors": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
 
@@ -301,6 +305,9 @@ class Context:
         t = Timing()
         _check(lib().cq_get_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def timing_reset(self):
+        _check(lib().cq_timing_reset(self._h))
 
     def bench_random_sectors(self, n_probes, iters=3):
         v = C.c_double()

@@ -44,7 +44,10 @@ struct cq_ctx {
 	int n_sms = 0;
 	cudaStream_t stream = NULL;
 	bool own_stream = false;
-	cudaEvent_t ev[6] = {NULL, NULL, NULL, NULL, NULL, NULL};
+	cudaEvent_t ev[2] = {NULL, NULL}; // H2D bracket of the last cq_reads_stage
+	struct StepEvents { cudaEvent_t e[4]; }; // pack start | scan start | scan end | reduce end
+	std::vector<StepEvents> steps;
+	size_t steps_used = 0;
 	// resident index
 	bool has_index = false;
 	uint32_t h = 0, n_genomes = 0;
@@ -248,7 +251,7 @@ extern "C" int cq_ctx_create(int device, void *stream, cq_ctx **out) {
 		}
 		c->own_stream = true;
 	}
-	for (int i = 0; i < 6; i++)
+	for (int i = 0; i < 2; i++)
 		cudaEventCreate(&c->ev[i]);
 	*out = c;
 	return CQ_OK;
@@ -264,8 +267,11 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	cudaFree(c->d_len); cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
 	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
 	cudaFree(c->d_leaf_d);
-	for (int i = 0; i < 6; i++)
+	for (int i = 0; i < 2; i++)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (auto &se : c->steps)
+		for (int i = 0; i < 4; i++)
+			cudaEventDestroy(se.e[i]);
 	if (c->own_stream)
 		cudaStreamDestroy(c->stream);
 	delete c;
@@ -311,7 +317,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaMalloc((void **) &c->d_counts, (ncnt + 4) * sizeof(unsigned long long)));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u, std::max<size_t>(c->n_leaves_u, 1) * 4));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d, std::max<size_t>(c->n_leaves_d, 1) * 4));
-	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, sizeof(unsigned long long)));
+	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 4 * sizeof(unsigned long long)));
 
 	// launch geometry: persistent grid, a whole number of CTAs per SM
 	c->smem_counters = n_genomes <= kMaxSmemGenomes;
@@ -340,8 +346,7 @@ extern "C" int cq_reset(cq_ctx *c) {
 	CQ_CUDA(cudaMemsetAsync(c->d_counts, 0, (ncnt + 4) * sizeof(unsigned long long), c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_u, 0, std::max<size_t>(c->n_leaves_u, 1) * 4, c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_d, 0, std::max<size_t>(c->n_leaves_d, 1) * 4, c->stream));
-	CQ_CUDA(cudaStreamSynchronize(c->stream));
-	return CQ_OK;
+	return CQ_OK; // stream-ordered; every reader of the counters is on the same stream
 }
 
 template <typename T>
@@ -358,6 +363,28 @@ static int ensure(T **ptr, size_t *cap, size_t need) {
 }
 
 // ------------------------------------------------------------------------------- query
+
+// Fold the CUDA events of the steps issued so far into the timing sums (synchronises).
+static int foldStepEvents(cq_ctx *c) {
+	if (c->steps_used == 0)
+		return CQ_OK;
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	for (size_t i = 0; i < c->steps_used; i++) {
+		float pack = 0, scan = 0, red = 0;
+		CQ_CUDA(cudaEventElapsedTime(&pack, c->steps[i].e[0], c->steps[i].e[1]));
+		CQ_CUDA(cudaEventElapsedTime(&scan, c->steps[i].e[1], c->steps[i].e[2]));
+		CQ_CUDA(cudaEventElapsedTime(&red, c->steps[i].e[2], c->steps[i].e[3]));
+		c->timing.pack_ms = pack;
+		c->timing.scan_ms = scan;
+		c->timing.reduce_ms = red;
+		c->timing.pack_ms_sum += pack;
+		c->timing.scan_ms_sum += scan;
+		c->timing.reduce_ms_sum += red;
+		c->timing.steps++;
+	}
+	c->steps_used = 0;
+	return CQ_OK;
+}
 
 extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads) {
@@ -439,8 +466,19 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		CQ_CUDA(cudaMemsetAsync(c->d_leaf_d, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 	}
 
-	CQ_CUDA(cudaEventRecord(c->ev[2], c->stream));
-	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 8, c->stream));
+	if (c->steps_used == c->steps.size()) {
+		if (c->steps.size() >= 1024) {
+			if ((rc = foldStepEvents(c)) != 0) return rc;
+		} else {
+			cq_ctx::StepEvents se;
+			for (int i = 0; i < 4; i++)
+				CQ_CUDA(cudaEventCreate(&se.e[i]));
+			c->steps.push_back(se);
+		}
+	}
+	cudaEvent_t *sev = c->steps[c->steps_used++].e;
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 32, c->stream));
+	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	if (n > 0) {
 		PackParams pp;
 		pp.bases = c->d_bases;
@@ -458,7 +496,7 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		pack_reads_kernel<<<pgrid, 256, 0, c->stream>>>(pp);
 		c->timing.kernel_launches++;
 	}
-	CQ_CUDA(cudaEventRecord(c->ev[3], c->stream));
+	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	if (n > 0) {
 		ScanParams sp;
 		memset(&sp, 0, sizeof(sp));
@@ -502,13 +540,13 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		c->timing.kernel_launches++;
 		c->timing.scan_launches++;
 	}
-	CQ_CUDA(cudaEventRecord(c->ev[4], c->stream));
+	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
 	if (n > 0 && c->smem_counters) {
 		reduce_partials_kernel<<<(unsigned) ((ncnt + 255) / 256), 256, 0, c->stream>>>(
 			c->d_partials, (uint32_t) c->grid, (uint32_t) ncnt, c->d_counts);
 		c->timing.kernel_launches++;
 	}
-	CQ_CUDA(cudaEventRecord(c->ev[5], c->stream));
+	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
 	CQ_CUDA(cudaGetLastError());
 	return CQ_OK;
 }
@@ -631,16 +669,28 @@ extern "C" int cq_get_timing(cq_ctx *c, cq_timing *out) {
 	CQ_CUDA(cudaStreamSynchronize(c->stream));
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timing.h2d_ms = ms;
-	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timing.pack_ms = ms;
-	if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->timing.scan_ms = ms;
-	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timing.reduce_ms = ms;
 	cudaGetLastError();
+	int rc = foldStepEvents(c);
+	if (rc != 0) return rc;
 	if (c->d_probe_count) {
-		unsigned long long pc = 0;
-		CQ_CUDA(cudaMemcpy(&pc, c->d_probe_count, 8, cudaMemcpyDeviceToHost));
-		c->timing.probes = pc;
+		unsigned long long pc[4] = {0, 0, 0, 0};
+		CQ_CUDA(cudaMemcpy(pc, c->d_probe_count, 32, cudaMemcpyDeviceToHost));
+		c->timing.probes = pc[0];
+		c->timing.bucket_hits = pc[1];
+		c->timing.leaf_hits = pc[2];
+		c->timing.chained_loads = pc[3];
 	}
 	*out = c->timing;
+	return CQ_OK;
+}
+
+extern "C" int cq_timing_reset(cq_ctx *c) {
+	if (c == NULL)
+		return fail(CQ_EINVAL, "cq_timing_reset: NULL context.");
+	int rc = foldStepEvents(c);
+	if (rc != 0) return rc;
+	c->timing.pack_ms_sum = c->timing.scan_ms_sum = c->timing.reduce_ms_sum = 0;
+	c->timing.steps = 0;
 	return CQ_OK;
 }
 

@@ -48,7 +48,7 @@ struct ScanParams {
 	uint32_t *rcount_u, *rcount_d;
 	unsigned long long *pair_records; // SC: (a<<32|b) per D_PAIR read
 	uint32_t *spill;          // [total warps][kSpillCap]
-	unsigned long long *probe_count;
+	unsigned long long *probe_count; // [4]: probes, bucket hits, leaf hits, extra (chained) bucket loads
 	// optional per-read outputs
 	uint8_t *read_class;
 	uint32_t *read_rid_a, *read_rid_b;
@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reads_kernel(ScanParams p) 
 	const uint32_t h = p.h, wpr = p.words_per_read;
 	const uint32_t lt_mask = (1u << lane) - 1;
 	unsigned long long n_undet = 0, n_conf = 0, n_probes = 0;
+	uint32_t n_bucket_hits = 0, n_leaf_hits = 0, n_chained = 0; // per lane
 
 	for (uint64_t r = warp; r < p.n_reads; r += n_warps) {
 		const uint32_t rl = p.len[r];
@@ -267,14 +268,17 @@ __global__ void __launch_bounds__(kScanThreads) scan_reads_kernel(ScanParams p) 
 								if (found || k0[u] == kEmptyKey || k1[u] == kEmptyKey)
 									break;
 								bidx[u] = (bidx[u] + 1) & p.table_mask; // full bucket: next one
+								n_chained++;
 								loadBucket(p.table + 2 * bidx[u], k0[u], r0[u], k1[u], r1[u]);
 							}
 							if (found) {
+								n_bucket_hits++;
 								const unsigned long long *w = q >= npos ? s.rev : s.fwd;
 								uint32_t pos = q >= npos ? q - npos : q;
 								uint32_t next = pos + h, remaining = rl - h - pos;
 								leaf_u = descend((uint32_t) refs, p.nodes_u, w, next, remaining);
 								leaf_d = descend((uint32_t) (refs >> 32), p.nodes_d, w, next, remaining);
+								n_leaf_hits += (leaf_u != kRefNone) + (leaf_d != kRefNone);
 							}
 						}
 						// append hits (U entries keep bit 31 clear, D entries set it)
@@ -434,10 +438,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_reads_kernel(ScanParams p) 
 		__syncwarp();
 	}
 
+	n_bucket_hits = __reduce_add_sync(0xffffffffu, n_bucket_hits);
+	n_leaf_hits = __reduce_add_sync(0xffffffffu, n_leaf_hits);
+	n_chained = __reduce_add_sync(0xffffffffu, n_chained);
 	if (lane == 0) {
 		if (n_undet) atomicAdd(&block_tot[0], n_undet);
 		if (n_conf) atomicAdd(&block_tot[1], n_conf);
-		if (n_probes) atomicAdd(p.probe_count, n_probes);
+		if (n_probes) atomicAdd(&p.probe_count[0], n_probes);
+		if (n_bucket_hits) atomicAdd(&p.probe_count[1], (unsigned long long) n_bucket_hits);
+		if (n_leaf_hits) atomicAdd(&p.probe_count[2], (unsigned long long) n_leaf_hits);
+		if (n_chained) atomicAdd(&p.probe_count[3], (unsigned long long) n_chained);
 	}
 	__syncthreads();
 	if (p.smem_counters) {

@@ -213,8 +213,15 @@ typedef struct {
 	double h2d_ms, pack_ms, scan_ms, reduce_ms, d2h_ms, total_ms; /* last cq_query / cq_query_staged */
 	uint64_t scan_launches, kernel_launches;                      /* since ctx creation */
 	uint64_t probes;  /* prefix-table probes issued by the last scan (2*(rl-h+1) per valid read) */
+	uint64_t bucket_hits, leaf_hits; /* last scan: probes whose h-mer is a key / leaves reached */
+	uint64_t chained_loads;          /* last scan: extra bucket loads after a full bucket */
+	/* CUDA-event durations summed over every step since cq_timing_reset (or ctx creation) */
+	double pack_ms_sum, scan_ms_sum, reduce_ms_sum;
+	uint64_t steps;
 } cq_timing;
+/* Synchronises the stream, folds the per-step CUDA events into the sums and returns them. */
 int cq_get_timing(cq_ctx *ctx, cq_timing *out);
+int cq_timing_reset(cq_ctx *ctx);
 
 /* Random 32-byte-sector gather micro-benchmark over the resident prefix table: the
    measured "lookup roofline" of SURVEY.md section 8d.  n_probes random bucket reads;

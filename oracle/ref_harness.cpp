@@ -15,7 +15,10 @@
  *
  * Usage:
  *   ref_harness dump <idx_u> <idx_d> <map> <p|mt|sc> <nthreads> <per_read_n> <out> <fastq>...
- *   ref_harness time <idx_u> <idx_d> <map> <p|mt|sc> <nthreads> <fastq>
+ *   ref_harness time <idx_u> <idx_d> <map> <p|mt|sc> <nthreads> <fastq> [reps]
+ *       prints one JSON line per repetition (the reference's own scan, timed around the
+ *       query64_* call like its "Time for query" bracket) and leaves with _exit so that the
+ *       pointer-trie teardown (tens of seconds at 3e7 leaves) is not waited for
  *
  * Canonical leaf ids in the dump = rank of the leaf's full key (h-base bucket prefix +
  * trie path) in lexicographic order within its table; both sides can compute it
@@ -139,6 +142,12 @@ int main(int argc, char **argv) {
 	}
 	for (; a < argc; a++)
 		fastqs.push_back(argv[a]);
+	int reps = 1;
+	if (cmd == "time" && fastqs.size() > 1) {
+		reps = atoi(fastqs.back().c_str());
+		fastqs.pop_back();
+		if (reps < 1) reps = 1;
+	}
 	if (fastqs.empty() || (mode != "p" && mode != "mt" && mode != "sc")) {
 		fprintf(stderr, "bad arguments\n");
 		return 2;
@@ -159,14 +168,28 @@ int main(int argc, char **argv) {
 
 	if (cmd == "time") {
 		fq.getFqnameWithoutDir(0);
-		auto t1 = std::chrono::high_resolution_clock::now();
-		runQuery(fq, mode, 0);
-		double q_ms = std::chrono::duration<double, std::milli>(
-			std::chrono::high_resolution_clock::now() - t1).count();
-		printf("{\"reads\": %zu, \"query_ms\": %.3f, \"load_ms\": %.3f, \"threads\": %d, \"mode\": \"%s\", "
-			"\"nundet\": %zu, \"nconf\": %zu}\n", fq.reads[0].size(), q_ms, load_ms, nthreads,
-			mode.c_str(), fq.nundet, fq.nconf);
-		return 0;
+		for (int rep = 0; rep < reps; rep++) {
+			auto t1 = std::chrono::high_resolution_clock::now();
+			runQuery(fq, mode, 0);
+			double q_ms = std::chrono::duration<double, std::milli>(
+				std::chrono::high_resolution_clock::now() - t1).count();
+			uint64_t su = 0, sd = 0;
+			for (size_t i = 1; i <= G; i++) {
+				su += fq.genomes[i]->read_cnts_u;
+				sd += fq.genomes[i]->read_cnts_d;
+			}
+			printf("{\"rep\": %d, \"reads\": %zu, \"query_ms\": %.3f, \"load_ms\": %.3f, \"threads\": %d, "
+				"\"mode\": \"%s\", \"nundet\": %zu, \"nconf\": %zu, \"sum_u\": %lu, \"sum_d\": %lu}\n",
+				rep, fq.reads[0].size(), q_ms, load_ms, nthreads, mode.c_str(), fq.nundet, fq.nconf,
+				(unsigned long) su, (unsigned long) sd);
+			fflush(stdout);
+			if (rep + 1 < reps) {
+				if (mode == "sc") fq.resetCounters_sc();
+				else fq.resetCounters();
+			}
+		}
+		fflush(stderr);
+		_exit(0);
 	}
 
 	FILE *out = fopen(out_fn.c_str(), "w");
