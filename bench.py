@@ -244,6 +244,8 @@ def main():
     d = workdir_for(name, w, args.workdir)
     idx = cq.Index(os.path.join(d, "index_u.bin1"), os.path.join(d, "index_d.bin2"))
     info = idx.info
+    # everything (kernels, memsets, NCCL hand-off, the timing events) runs on one torch stream
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream().cuda_stream
     ctx = cq.Context(local, stream=stream).upload(idx, w["n_genomes"])
     t_index = time.time() - t0

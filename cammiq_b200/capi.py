@@ -65,6 +65,13 @@ class DeviceCounters(C.Structure):
                 ("n_rcount_u", C.c_uint64), ("d_rcount_d", C.c_void_p), ("n_rcount_d", C.c_uint64)]
 
 
+class DeviceInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
+                ("l2_bytes", C.c_uint64), ("persisting_l2_max_bytes", C.c_uint64),
+                ("access_policy_max_window_bytes", C.c_uint64), ("global_mem_bytes", C.c_uint64),
+                ("sm_clock_khz", C.c_int), ("mem_clock_khz", C.c_int), ("mem_bus_bits", C.c_int)]
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("pack_ms", C.c_double), ("scan_ms", C.c_double),
                 ("reduce_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
@@ -100,6 +107,9 @@ SYMBOLS = {
     "cq_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "cq_timing_reset": (C.c_int, [C.c_void_p]),
     "cq_bench_random_sectors": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "cq_bench_random_gather": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double)]),
+    "cq_get_device_info": (C.c_int, [C.c_void_p, C.POINTER(DeviceInfo)]),
 }
 
 _LIB = None
@@ -194,7 +204,10 @@ class Context:
     def __init__(self, device=0, stream=None):
         self._h = C.c_void_p()
         self.device = device
-        _check(lib().cq_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        # stream: None -> the context creates its own; an integer cudaStream_t handle otherwise
+        # (0, the legacy default stream as torch reports it, is passed as cudaStreamLegacy = 1)
+        handle = None if stream is None else C.c_void_p(stream if stream != 0 else 1)
+        _check(lib().cq_ctx_create(device, handle, C.byref(self._h)))
         self.n_genomes = 0
         self.index = None
 
@@ -313,6 +326,19 @@ class Context:
         v = C.c_double()
         _check(lib().cq_bench_random_sectors(self._h, n_probes, iters, C.byref(v)))
         return v.value
+
+    def bench_random_gather(self, region_bytes, access_bytes, n_probes, iters=3, persist=False):
+        v = C.c_double()
+        _check(lib().cq_bench_random_gather(self._h, region_bytes, access_bytes, n_probes, iters,
+                                            1 if persist else 0, C.byref(v)))
+        return v.value
+
+    def device_info(self):
+        d = DeviceInfo()
+        _check(lib().cq_get_device_info(self._h, C.byref(d)))
+        out = {k: getattr(d, k) for k, _ in DeviceInfo._fields_}
+        out["name"] = out["name"].decode()
+        return out
 
     def close(self):
         if self._h:

@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/cammiq_gpu.h"
@@ -715,5 +716,88 @@ extern "C" int cq_bench_random_sectors(cq_ctx *c, uint64_t n_probes, int iters, 
 	cudaEventDestroy(b);
 	*gsectors_per_s = (double) n_probes * iters / (ms * 1e-3) * 1e-9;
 	c->timing.kernel_launches += iters + 1;
+	return CQ_OK;
+}
+
+extern "C" int cq_bench_random_gather(cq_ctx *c, uint64_t region_bytes, int access_bytes, uint64_t n_probes,
+		int iters, int persist, double *gaccesses_per_s) {
+	if (c == NULL || gaccesses_per_s == NULL || iters < 1 || region_bytes < 4096 ||
+		(region_bytes & (region_bytes - 1)) != 0 ||
+		(access_bytes != 4 && access_bytes != 8 && access_bytes != 16 && access_bytes != 32))
+		return fail(CQ_EINVAL, "cq_bench_random_gather: bad argument.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	uint8_t *region = NULL;
+	unsigned long long *sink = NULL;
+	CQ_CUDA(cudaMalloc((void **) &region, region_bytes));
+	CQ_CUDA(cudaMalloc((void **) &sink, 8));
+	CQ_CUDA(cudaMemsetAsync(region, 1, region_bytes, c->stream));
+	if (persist) {
+		cudaDeviceProp prop;
+		CQ_CUDA(cudaGetDeviceProperties(&prop, c->device));
+		CQ_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize));
+		cudaStreamAttrValue attr;
+		memset(&attr, 0, sizeof(attr));
+		attr.accessPolicyWindow.base_ptr = region;
+		attr.accessPolicyWindow.num_bytes = std::min<size_t>(region_bytes, prop.accessPolicyMaxWindowSize);
+		attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float) prop.persistingL2CacheMaxSize / (float) region_bytes);
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		CQ_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+	}
+	const uint64_t mask = (region_bytes - 1) & ~(uint64_t) (access_bytes - 1);
+	const int grid = c->n_sms * 8;
+	auto launch = [&](uint64_t seed) {
+		switch (access_bytes) {
+		case 4: random_gather_kernel<4><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		case 8: random_gather_kernel<8><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		case 16: random_gather_kernel<16><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		default: random_gather_kernel<32><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		}
+	};
+	launch(1);
+	launch(2);
+	cudaEvent_t a, b;
+	CQ_CUDA(cudaEventCreate(&a));
+	CQ_CUDA(cudaEventCreate(&b));
+	CQ_CUDA(cudaEventRecord(a, c->stream));
+	for (int i = 0; i < iters; i++)
+		launch(1000 + 7919ull * i);
+	CQ_CUDA(cudaEventRecord(b, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	CQ_CUDA(cudaEventElapsedTime(&ms, a, b));
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	if (persist) {
+		cudaStreamAttrValue attr;
+		memset(&attr, 0, sizeof(attr));
+		attr.accessPolicyWindow.num_bytes = 0;
+		cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+		cudaCtxResetPersistingL2Cache();
+	}
+	cudaFree(region);
+	cudaFree(sink);
+	*gaccesses_per_s = (double) n_probes * iters / (ms * 1e-3) * 1e-9;
+	c->timing.kernel_launches += iters + 2;
+	return CQ_OK;
+}
+
+extern "C" int cq_get_device_info(cq_ctx *c, cq_device_info *out) {
+	if (c == NULL || out == NULL)
+		return fail(CQ_EINVAL, "cq_get_device_info: NULL argument.");
+	cudaDeviceProp prop;
+	CQ_CUDA(cudaGetDeviceProperties(&prop, c->device));
+	memset(out, 0, sizeof(*out));
+	strncpy(out->name, prop.name, sizeof(out->name) - 1);
+	out->sm_count = prop.multiProcessorCount;
+	out->cc_major = prop.major;
+	out->cc_minor = prop.minor;
+	out->l2_bytes = (uint64_t) prop.l2CacheSize;
+	out->persisting_l2_max_bytes = (uint64_t) prop.persistingL2CacheMaxSize;
+	out->access_policy_max_window_bytes = (uint64_t) prop.accessPolicyMaxWindowSize;
+	out->global_mem_bytes = (uint64_t) prop.totalGlobalMem;
+	out->sm_clock_khz = prop.clockRate;
+	out->mem_clock_khz = prop.memoryClockRate;
+	out->mem_bus_bits = prop.memoryBusWidth;
 	return CQ_OK;
 }

@@ -497,5 +497,33 @@ __global__ void __launch_bounds__(256) random_sector_kernel(const TableSlot *tab
 		*sink = acc;
 }
 
+template <int BYTES>
+__global__ void __launch_bounds__(256) random_gather_kernel(const uint8_t *region, uint64_t mask,
+		uint64_t n_probes, uint64_t seed, unsigned long long *sink) {
+	const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t n_threads = (uint64_t) gridDim.x * blockDim.x;
+	unsigned long long acc = 0;
+	for (uint64_t i = tid; i < n_probes; i += n_threads * kProbeUnroll) {
+		unsigned long long v[kProbeUnroll][4];
+#pragma unroll
+		for (int u = 0; u < kProbeUnroll; u++) {
+			uint64_t j = i + (uint64_t) u * n_threads;
+			v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0;
+			if (j < n_probes) {
+				const uint8_t *a = region + ((mixKey(j + seed) * BYTES) & mask);
+				if (BYTES == 4) { unsigned int t; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(t) : "l"(a)); v[u][0] = t; }
+				else if (BYTES == 8) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v[u][0]) : "l"(a));
+				else if (BYTES == 16) asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(v[u][0]), "=l"(v[u][1]) : "l"(a));
+				else asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[u][0]), "=l"(v[u][1]), "=l"(v[u][2]), "=l"(v[u][3]) : "l"(a));
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < kProbeUnroll; u++)
+			acc += v[u][0] ^ v[u][1] ^ v[u][2] ^ v[u][3];
+	}
+	if (acc == 0x123456789ull)
+		*sink = acc;
+}
+
 } // namespace cammiq
 #endif

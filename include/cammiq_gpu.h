@@ -228,6 +228,20 @@ int cq_timing_reset(cq_ctx *ctx);
    *gsectors_per_s receives 1e-9 * sectors/s (CUDA-event timed). */
 int cq_bench_random_sectors(cq_ctx *ctx, uint64_t n_probes, int iters, double *gsectors_per_s);
 
+/* Same measurement over a scratch region of region_bytes (power of two) read with
+   access_bytes = 4, 8, 16 or 32 per probe: maps out the L2 / HBM random-access curve that
+   sizes the resident filter.  persist != 0 pins the region with an L2 access-policy window. */
+int cq_bench_random_gather(cq_ctx *ctx, uint64_t region_bytes, int access_bytes, uint64_t n_probes,
+		int iters, int persist, double *gaccesses_per_s);
+
+typedef struct {
+	char name[128];
+	int sm_count, cc_major, cc_minor;
+	uint64_t l2_bytes, persisting_l2_max_bytes, access_policy_max_window_bytes, global_mem_bytes;
+	int sm_clock_khz, mem_clock_khz, mem_bus_bits;
+} cq_device_info;
+int cq_get_device_info(cq_ctx *ctx, cq_device_info *out);
+
 #ifdef __cplusplus
 }
 #endif
