@@ -37,7 +37,7 @@ class IndexInfo(C.Structure):
     _fields_ = [("hash_len", C.c_uint32), ("n_leaves_u", C.c_uint64), ("n_leaves_d", C.c_uint64),
                 ("n_buckets_u", C.c_uint64), ("n_buckets_d", C.c_uint64), ("n_keys", C.c_uint64),
                 ("n_table_buckets", C.c_uint64), ("n_nodes_u", C.c_uint64), ("n_nodes_d", C.c_uint64),
-                ("max_ref_id", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("max_ref_id", C.c_uint32), ("filter_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("decode_ms", C.c_double), ("flatten_ms", C.c_double)]
 
 
@@ -88,6 +88,7 @@ SYMBOLS = {
     "cq_index_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_void_p)]),
     "cq_index_free": (None, [C.c_void_p]),
     "cq_index_get_info": (C.c_int, [C.c_void_p, C.POINTER(IndexInfo)]),
+    "cq_index_set_filter_budget": (C.c_int, [C.c_void_p, C.c_uint64]),
     "cq_index_leaves": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(LeafView)]),
     "cq_index_map_sp": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_uint64)]),
@@ -157,6 +158,10 @@ class Index:
         self.info = info
         self.hash_len = info.hash_len
         self.n_leaves_u, self.n_leaves_d = info.n_leaves_u, info.n_leaves_d
+
+    def set_filter_budget(self, max_bytes):
+        _check(lib().cq_index_set_filter_budget(self._h, max_bytes))
+        _check(lib().cq_index_get_info(self._h, C.byref(self.info)))
 
     def leaves(self, table):
         v = LeafView()

@@ -60,7 +60,10 @@ struct cq_ctx {
 	unsigned long long *d_counts = NULL; // 2*(G+1)+4
 	uint32_t *d_rcount_u = NULL, *d_rcount_d = NULL;
 	uint32_t *d_partials = NULL;
-	uint32_t *d_spill = NULL;
+	uint32_t *d_spill = NULL; // per-read hit overflow, [max grid warps][32][kHitSpill]
+	uint2 *d_filter = NULL;
+	uint64_t filter_mask = 0;
+	int max_grid = 0;
 	unsigned long long *d_probe_count = NULL;
 	int grid = 0;
 	bool smem_counters = true;
@@ -72,10 +75,7 @@ struct cq_ctx {
 	size_t cap_bases = 0, cap_reads_off = 0, cap_reads_len = 0;
 	uint64_t staged_reads = 0, staged_stride = 0, staged_bytes = 0;
 	bool staged_has_offsets = false;
-	uint32_t staged_wpr = 0;
-	uint64_t *d_packed = NULL;
-	uint8_t *d_len = NULL;
-	size_t cap_packed = 0, cap_len = 0;
+	uint32_t staged_max_len = 0;
 	// SC pair records (device, grows)
 	unsigned long long *d_pairs = NULL;
 	size_t cap_pairs = 0;
@@ -150,9 +150,21 @@ extern "C" int cq_index_get_info(const cq_index *idx, cq_index_info *info) {
 	info->n_nodes_u = f.u.numNodes();
 	info->n_nodes_d = f.d.numNodes();
 	info->max_ref_id = std::max(f.u.max_ref_id, f.d.max_ref_id);
+	info->filter_bytes = f.filter.size() * 8;
 	info->device_bytes = f.deviceBytes();
 	info->decode_ms = f.decode_ms;
 	info->flatten_ms = f.flatten_ms;
+	return CQ_OK;
+}
+
+extern "C" int cq_index_set_filter_budget(cq_index *idx, uint64_t max_bytes) {
+	if (idx == NULL)
+		return fail(CQ_EINVAL, "cq_index_set_filter_budget: NULL index.");
+	try {
+		buildFilter(idx->flat, max_bytes);
+	} catch (const std::bad_alloc &) {
+		return fail(CQ_ENOMEM, "cq_index_set_filter_budget: out of memory.");
+	}
 	return CQ_OK;
 }
 
@@ -213,7 +225,8 @@ static void freeDevice(cq_ctx *c) {
 	cudaFree(c->d_table); cudaFree(c->d_nodes_u); cudaFree(c->d_nodes_d);
 	cudaFree(c->d_leaf_u_ref); cudaFree(c->d_leaf_d_ref); cudaFree(c->d_counts);
 	cudaFree(c->d_rcount_u); cudaFree(c->d_rcount_d); cudaFree(c->d_partials);
-	cudaFree(c->d_spill); cudaFree(c->d_probe_count);
+	cudaFree(c->d_spill); cudaFree(c->d_probe_count); cudaFree(c->d_filter);
+	c->d_filter = NULL;
 	c->d_table = NULL; c->d_nodes_u = c->d_nodes_d = c->d_leaf_u_ref = NULL; c->d_leaf_d_ref = NULL;
 	c->d_counts = NULL; c->d_rcount_u = c->d_rcount_d = c->d_partials = c->d_spill = NULL;
 	c->d_probe_count = NULL;
@@ -264,8 +277,8 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	freeDevice(c);
-	cudaFree(c->d_bases); cudaFree(c->d_offsets); cudaFree(c->d_lengths); cudaFree(c->d_packed);
-	cudaFree(c->d_len); cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
+	cudaFree(c->d_bases); cudaFree(c->d_offsets); cudaFree(c->d_lengths);
+	cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
 	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
 	cudaFree(c->d_leaf_d);
 	for (int i = 0; i < 2; i++)
@@ -320,21 +333,19 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d, std::max<size_t>(c->n_leaves_d, 1) * 4));
 	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 4 * sizeof(unsigned long long)));
 
-	// launch geometry: persistent grid, a whole number of CTAs per SM
+	if (!f.filter.empty()) {
+		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), c->stream)) != 0) return rc;
+		c->filter_mask = f.filter.size() - 1;
+		CQ_CUDA(cudaStreamSynchronize(c->stream));
+	}
+	// block-private genome counters in shared memory when they fit, global atomics otherwise;
+	// the grid itself is sized per launch (it depends on the tile's shared-memory footprint)
 	c->smem_counters = n_genomes <= kMaxSmemGenomes;
 	c->smem_bytes = c->smem_counters ? ncnt * sizeof(uint32_t) : 0;
-	if (c->smem_bytes > 48 * 1024) {
-		CQ_CUDA(cudaFuncSetAttribute(scan_reads_kernel<CQ_MODE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem_bytes));
-		CQ_CUDA(cudaFuncSetAttribute(scan_reads_kernel<CQ_MODE_SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem_bytes));
-	}
-	int per_sm = 0;
-	CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_reads_kernel<CQ_MODE_P>, kScanThreads, c->smem_bytes));
-	if (per_sm < 1)
-		return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
-	c->grid = per_sm * c->n_sms;
+	c->max_grid = kMaxBlocksPerSM * c->n_sms;
 	if (c->smem_counters)
-		CQ_CUDA(cudaMalloc((void **) &c->d_partials, (size_t) c->grid * ncnt * sizeof(uint32_t)));
-	CQ_CUDA(cudaMalloc((void **) &c->d_spill, (size_t) c->grid * kWarpsPerBlock * kSpillCap * sizeof(uint32_t)));
+		CQ_CUDA(cudaMalloc((void **) &c->d_partials, (size_t) c->max_grid * ncnt * sizeof(uint32_t)));
+	CQ_CUDA(cudaMalloc((void **) &c->d_spill, (size_t) c->max_grid * kWarpsPerBlock * 32 * kHitSpill * sizeof(uint32_t)));
 	c->has_index = true;
 	return cq_reset(c);
 }
@@ -394,7 +405,7 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	if (n_reads > 0 && (bases == NULL || lengths == NULL))
 		return fail(CQ_EINVAL, "cq_reads_stage: NULL read buffers.");
 	CQ_CUDA(cudaSetDevice(c->device));
-	// extent of the base buffer and the longest read (sets the packed stride)
+	// extent of the base buffer and the longest read (sets the shared-memory tile size)
 	uint64_t total = 0;
 	uint32_t max_len = 1;
 	for (uint64_t i = 0; i < n_reads; i++) {
@@ -418,7 +429,7 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	c->staged_stride = stride;
 	c->staged_has_offsets = offsets != NULL;
 	c->staged_bytes = total;
-	c->staged_wpr = (max_len + 31) / 32;
+	c->staged_max_len = max_len;
 	return CQ_OK;
 }
 
@@ -429,10 +440,7 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		return fail(CQ_EINVAL, "cq_query_staged: bad mode.");
 	CQ_CUDA(cudaSetDevice(c->device));
 	const uint64_t n = c->staged_reads;
-	const uint32_t wpr = std::max<uint32_t>(c->staged_wpr, 1);
 	int rc;
-	if ((rc = ensure(&c->d_packed, &c->cap_packed, (size_t) n * wpr + 1)) != 0) return rc;
-	if ((rc = ensure(&c->d_len, &c->cap_len, (size_t) n)) != 0) return rc;
 	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
 	if (mode == CQ_MODE_SC) {
 		// worst case every read adds a pair record on top of those already held
@@ -480,23 +488,6 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 	cudaEvent_t *sev = c->steps[c->steps_used++].e;
 	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 32, c->stream));
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
-	if (n > 0) {
-		PackParams pp;
-		pp.bases = c->d_bases;
-		pp.offsets = c->staged_has_offsets ? c->d_offsets : NULL;
-		pp.stride = c->staged_stride;
-		pp.lengths = c->d_lengths;
-		pp.n_reads = n;
-		pp.words_per_read = wpr;
-		pp.h = c->h;
-		pp.packed = c->d_packed;
-		pp.len_out = c->d_len;
-		pp.n_invalid = c->d_counts + ncnt + 2;
-		uint64_t want_blocks = (n + 7) / 8;
-		int pgrid = (int) std::min<uint64_t>(want_blocks, (uint64_t) c->n_sms * 8);
-		pack_reads_kernel<<<pgrid, 256, 0, c->stream>>>(pp);
-		c->timing.kernel_launches++;
-	}
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	if (n > 0) {
 		ScanParams sp;
@@ -509,18 +500,25 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		sp.leaf_d_ref = c->d_leaf_d_ref;
 		sp.h = c->h;
 		sp.n_genomes = c->n_genomes;
-		sp.packed = c->d_packed;
-		sp.len = c->d_len;
-		sp.words_per_read = wpr;
+		sp.filter = c->d_filter;
+		sp.filter_mask = c->filter_mask;
+		sp.bases = c->d_bases;
+		sp.offsets = c->staged_has_offsets ? c->d_offsets : NULL;
+		sp.stride = c->staged_stride;
+		sp.lengths = c->d_lengths;
 		sp.n_reads = n;
-		sp.mode = mode;
+		// shared-memory tile: the byte range 256 back-to-back reads of the longest length span
+		// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
+		const uint32_t tile_cap = (kScanThreads * std::max<uint32_t>(c->staged_max_len, 1) + 32 + 127) & ~127u;
+		sp.tile_cap = tile_cap;
+		const size_t dyn_smem = tile_cap + c->smem_bytes;
 		sp.smem_counters = c->smem_counters ? 1 : 0;
 		sp.partials = c->d_partials;
 		sp.counts = c->d_counts;
 		sp.rcount_u = c->d_rcount_u;
 		sp.rcount_d = c->d_rcount_d;
 		sp.pair_records = c->d_pairs;
-		sp.spill = c->d_spill;
+		sp.hit_spill = c->d_spill;
 		sp.probe_count = c->d_probe_count;
 		if (c->want_per_read) {
 			sp.read_class = c->d_read_class;
@@ -534,10 +532,19 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 			sp.read_leaf_u = c->d_leaf_u;
 			sp.read_leaf_d = c->d_leaf_d;
 		}
-		if (mode == CQ_MODE_P)
-			scan_reads_kernel<CQ_MODE_P><<<c->grid, kScanThreads, c->smem_bytes, c->stream>>>(sp);
-		else
-			scan_reads_kernel<CQ_MODE_SC><<<c->grid, kScanThreads, c->smem_bytes, c->stream>>>(sp);
+		const bool filt = c->d_filter != NULL;
+		const void *kern = mode == CQ_MODE_P
+			? (filt ? (const void *) scan_reads_kernel<CQ_MODE_P, true> : (const void *) scan_reads_kernel<CQ_MODE_P, false>)
+			: (filt ? (const void *) scan_reads_kernel<CQ_MODE_SC, true> : (const void *) scan_reads_kernel<CQ_MODE_SC, false>);
+		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
+		int per_sm = 0;
+		CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScanThreads, dyn_smem));
+		if (per_sm < 1)
+			return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
+		const uint64_t n_tiles = (n + kScanThreads - 1) / kScanThreads;
+		c->grid = (int) std::min<uint64_t>((uint64_t) std::min(per_sm, kMaxBlocksPerSM) * c->n_sms, n_tiles);
+		void *args[] = {&sp};
+		CQ_CUDA(cudaLaunchKernel(kern, dim3(c->grid), dim3(kScanThreads), args, dyn_smem, c->stream));
 		c->timing.kernel_launches++;
 		c->timing.scan_launches++;
 	}

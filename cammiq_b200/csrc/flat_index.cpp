@@ -7,7 +7,7 @@
 namespace cammiq {
 
 uint64_t FlatIndex::deviceBytes() const {
-	return table.size() * sizeof(TableSlot) + (u.nodes.size() + d.nodes.size()) * 4 +
+	return table.size() * sizeof(TableSlot) + filter.size() * 8 + (u.nodes.size() + d.nodes.size()) * 4 +
 		u.numLeaves() * 4 + d.numLeaves() * 8 + (u.numLeaves() + d.numLeaves()) * 4;
 }
 
@@ -80,13 +80,46 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 	out.n_keys = n_keys;
 	out.u = std::move(u);
 	out.d = std::move(d);
+	buildFilter(out, kFilterMaxBytesDefault);
 	out.flatten_ms = std::chrono::duration<double, std::milli>(
 		std::chrono::high_resolution_clock::now() - t0).count();
 	return CQ_OK;
 }
 
+void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
+	fi.filter.clear();
+	fi.filter.shrink_to_fit();
+	if (max_bytes < 8192)
+		return;
+	// 16 bits per key when they fit, never fewer than kFilterMinBitsPerKey
+	uint64_t words = 1024;
+	while (words * 64 < fi.n_keys * 16 && words * 8 * 2 <= max_bytes)
+		words <<= 1;
+	if (words * 64 < fi.n_keys * kFilterMinBitsPerKey)
+		return; // would not fit L2 at a useful false-positive rate: probe the table directly
+	fi.filter.assign(words, 0);
+	const uint64_t wmask = words - 1;
+	for (size_t i = 0; i < fi.table.size(); i++) {
+		if (fi.table[i].key == kEmptyKey)
+			continue;
+		uint64_t w;
+		uint32_t lo, hi;
+		filterProbe(mixKey(fi.table[i].key), wmask, w, lo, hi);
+		fi.filter[w] |= (uint64_t) lo | ((uint64_t) hi << 32);
+	}
+}
+
 uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t *cand, size_t len) {
 	uint64_t mask = fi.n_table_buckets - 1;
+	if (!fi.filter.empty()) {
+		// same gate as phase 1 of the scan kernel: a filter miss ends the lookup
+		uint64_t w;
+		uint32_t lo, hi;
+		filterProbe(mixKey(bucket), fi.filter.size() - 1, w, lo, hi);
+		uint64_t m = (uint64_t) lo | ((uint64_t) hi << 32);
+		if ((fi.filter[w] & m) != m)
+			return UINT64_MAX;
+	}
 	uint64_t b = mixKey(bucket) & mask;
 	uint32_t ref = kRefNone;
 	for (;;) {

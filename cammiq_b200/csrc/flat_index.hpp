@@ -43,11 +43,31 @@ inline uint64_t mixKey(uint64_t x) {
 	return x;
 }
 
+// L2-resident membership filter in front of the table: register-blocked Bloom filter, one
+// 64-bit word per key (two bits in each 32-bit half).  ~98-99% of probes miss (SURVEY.md
+// Appendix A.6); a filter that fits the B200's L2 (random gathers over <= 64 MB run at
+// ~285 G/s versus ~45 G sectors/s from HBM, profiles/r01_microbench_gather.json) answers
+// them without touching DRAM.  Word index = bits 32.. of mixKey, bit selectors = its low 20
+// bits (independent of the word index).
+static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
+static const uint32_t kFilterMinBitsPerKey = 8;
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void filterProbe(uint64_t mixed, uint64_t word_mask, uint64_t &word, uint32_t &mask_lo, uint32_t &mask_hi) {
+	word = (mixed >> 32) & word_mask;
+	uint32_t m = (uint32_t) mixed;
+	mask_lo = (1u << (m & 31)) | (1u << ((m >> 5) & 31));
+	mask_hi = (1u << ((m >> 10) & 31)) | (1u << ((m >> 15) & 31));
+}
+
 struct FlatIndex {
 	uint32_t hash_len = 0;
 	uint64_t n_table_buckets = 0; // power of two
 	uint64_t n_keys = 0;
 	std::vector<TableSlot> table; // n_table_buckets * kSlotsPerBucket
+	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
 	double decode_ms = 0, flatten_ms = 0;
 
@@ -56,6 +76,9 @@ struct FlatIndex {
 
 // Build the merged prefix table from the two decoded indices (moved into out).
 int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatIndex &out, std::string &err);
+
+// (Re)build the membership filter with at most max_bytes (0 = no filter).
+void buildFilter(FlatIndex &fi, uint64_t max_bytes);
 
 // Hash::find64_p on the flattened layout (host; layout verification only).
 uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t *cand, size_t len);

@@ -82,6 +82,7 @@ typedef struct {
 	uint64_t n_nodes_u;      /* CSR trie nodes below non-leaf bucket roots */
 	uint64_t n_nodes_d;
 	uint32_t max_ref_id;     /* largest genome id stored in a leaf */
+	uint64_t filter_bytes;   /* membership filter size, 0 = none */
 	uint64_t device_bytes;   /* bytes cq_index_upload will place on the device */
 	double decode_ms, flatten_ms;
 } cq_index_info;
@@ -94,6 +95,14 @@ typedef struct {
 int cq_index_load(const char *path_u, const char *path_d, double load_factor, cq_index **out);
 void cq_index_free(cq_index *idx);
 int cq_index_get_info(const cq_index *idx, cq_index_info *info);
+/*
+ * (Re)build the L2-resident membership filter that fronts the prefix table, using at most
+ * max_bytes (a power of two is used; 0 removes the filter, so every position probes the
+ * table in HBM).  cq_index_load builds it with a 64 MB budget -- what the B200's L2 serves
+ * at full random-gather rate -- and drops it when fewer than 8 bits per key would fit.
+ * Takes effect at the next cq_index_upload.
+ */
+int cq_index_set_filter_budget(cq_index *idx, uint64_t max_bytes);
 
 /* Leaf fields in FILE order (leaf id = order of appearance in the index file). */
 typedef struct {

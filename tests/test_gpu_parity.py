@@ -21,8 +21,11 @@ def ctx():
     c.close()
 
 
-def run_gpu(ctx, c, mode, load_factor=0.0, **kw):
+def run_gpu(ctx, c, mode, load_factor=0.0, filter_bytes=None, **kw):
     idx = cq.Index(c["iu"], c["id"], load_factor)
+    if filter_bytes is not None:
+        idx.set_filter_budget(filter_bytes)
+        assert (idx.info.filter_bytes > 0) == (filter_bytes > 0)
     ctx.upload(idx, c["G"])
     return idx, ctx.query(cq.MODE_SC if mode == "sc" else cq.MODE_P, c["bases"], c["offsets"],
                           c["lengths"], **kw)
@@ -50,8 +53,10 @@ def test_gpu_matches_oracle_every_read(ctx, case, mode):
     m = ol.MODE_SC if mode == "sc" else ol.MODE_P
     want = ol.oracle_query(oi_u, oi_d, m, c["G"], c["bases"], c["offsets"], c["lengths"],
                            per_read=True, leaf_cap=128)
-    for lf in (0.0, 0.95):
-        idx, got = run_gpu(ctx, c, mode, load_factor=lf, per_read=True, leaf_cap=128)
+    # default filter; no filter (table probed in phase 1) with chained buckets; a tiny filter
+    # with a high false-positive rate
+    for lf, fb in ((0.0, None), (0.95, 0), (0.95, 8192)):
+        idx, got = run_gpu(ctx, c, mode, load_factor=lf, filter_bytes=fb, per_read=True, leaf_cap=128)
         for k in ("nundet", "nconf", "n_invalid"):
             assert int(got[k]) == int(want[k]), (k, lf)
         for k in ("cnt_u", "cnt_d", "read_class", "read_rid_a", "read_rid_b", "read_nleaf_u",
@@ -140,8 +145,10 @@ def test_dense_index_spills_hit_list(ctx, tmp_path):
     for mode, m in ((cq.MODE_P, ol.MODE_P), (cq.MODE_SC, ol.MODE_SC)):
         want = ol.oracle_query(oi_u, oi_d, m, G, b, o, l, per_read=True, leaf_cap=600)
         assert int((want["read_nleaf_u"] + want["read_nleaf_d"]).max()) > 100
-        for lf in (0.0, 1.0):
+        for lf, fb in ((0.0, None), (1.0, 0)):
             idx = cq.Index(pu, pd, lf)
+            if fb is not None:
+                idx.set_filter_budget(fb)
             ctx.upload(idx, G)
             got = ctx.query(mode, b, o, l, per_read=True, leaf_cap=600)
             for k in ("read_class", "read_rid_a", "read_rid_b", "read_nleaf_u", "read_nleaf_d",
