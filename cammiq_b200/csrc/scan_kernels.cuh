@@ -89,10 +89,36 @@ __device__ __forceinline__ void loadBucket(const TableSlot *b, unsigned long lon
 		: "=l"(k0), "=l"(r0), "=l"(k1), "=l"(r1) : "l"(b));
 }
 
-__device__ __forceinline__ uint2 loadFilterWord(const uint2 *f) {
+// L2 residency is the whole point of the filter: its words are loaded with an evict_last
+// policy while every streaming access of the kernel (table sectors, leaf ids, rcount
+// updates, the read tiles) is issued evict_first, so the 64 MB filter is what the L2 keeps.
+__device__ __forceinline__ unsigned long long policyEvictLast() {
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ unsigned long long policyEvictFirst() {
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ uint2 loadFilterWord(const uint2 *f, unsigned long long policy) {
 	uint2 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(f));
+	asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(f), "l"(policy));
 	return v;
+}
+__device__ __forceinline__ uint32_t loadStreamU32(const uint32_t *a) {
+	uint32_t v;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(a));
+	return v;
+}
+__device__ __forceinline__ uint2 loadStreamU32x2(const uint2 *a) {
+	uint2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
+	return v;
+}
+__device__ __forceinline__ void redAddStream(uint32_t *a, unsigned long long policy) {
+	asm volatile("red.global.add.L2::cache_hint.u32 [%0], 1, %1;" ::"l"(a), "l"(policy) : "memory");
 }
 
 __device__ __forceinline__ uint32_t smemAddr(const void *p) {
@@ -107,9 +133,9 @@ __device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulkCopyG2S(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+__device__ __forceinline__ void bulkCopyG2S(void *dst, const void *src, uint32_t bytes, uint64_t *bar, unsigned long long policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+		::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
 	asm volatile(
@@ -144,7 +170,7 @@ __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__rest
 		if (next >= rl)
 			return kRefNone;
 		uint32_t code = strandBase(s, rl, strand, next);
-		ref = __ldg(&nodes[4 * (size_t) (ref - 1) + code]);
+		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
 		next++;
 	}
 	return ref;
@@ -227,6 +253,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 	__syncthreads();
 
 	const uint32_t h = p.h;
+	const unsigned long long pol_keep = policyEvictLast(), pol_stream = policyEvictFirst();
 	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
 	const uint32_t top_shift = 2 * h - 2;
 	uint32_t *warp_spill = p.hit_spill + ((size_t) blockIdx.x * kWarpsPerBlock + wib) * 32 * kHitSpill;
@@ -267,7 +294,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 		if (staged) {
 			if (tid == 0) {
 				mbarExpectTx(&tile_bar, (uint32_t) bytes);
-				bulkCopyG2S(tile, p.bases + start, (uint32_t) bytes, &tile_bar);
+				bulkCopyG2S(tile, p.bases + start, (uint32_t) bytes, &tile_bar, pol_stream);
 			}
 			mbarWait(&tile_bar, bar_parity);
 			bar_parity ^= 1u;
@@ -309,8 +336,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 						uint64_t wf, wr;
 						filterProbe(xf, p.filter_mask, wf, mf[u][0], mf[u][1]);
 						filterProbe(xr, p.filter_mask, wr, mr[u][0], mr[u][1]);
-						ff[u] = loadFilterWord(p.filter + wf);
-						fr[u] = loadFilterWord(p.filter + wr);
+						ff[u] = loadFilterWord(p.filter + wf, pol_keep);
+						fr[u] = loadFilterWord(p.filter + wr, pol_keep);
 					} else {
 						loadBucket(p.table + 2 * (xf & p.table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
 						loadBucket(p.table + 2 * (xr & p.table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
@@ -363,13 +390,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 			for (uint32_t i = 0; i < nh; i++) {
 				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
 				if (e & kRefLeafTag) {
-					uint2 ab = __ldg(&p.leaf_d_ref[e & ~kRefLeafTag]);
+					uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
 					uint32_t l = min(ab.x, ab.y), g = max(ab.x, ab.y);
 					unsigned long long key = ((unsigned long long) l << 32) | g;
 					min_p = key < min_p ? key : min_p;
 					max_p = key > max_p ? key : max_p;
 				} else {
-					uint32_t rid = __ldg(&p.leaf_u_ref[e]);
+					uint32_t rid = loadStreamU32(&p.leaf_u_ref[e]);
 					min_r = min(min_r, rid);
 					max_r = max(max_r, rid);
 				}
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 				for (uint32_t i = 0; i < nh; i++) {
 					uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
 					if (e & kRefLeafTag) {
-						uint2 ab = __ldg(&p.leaf_d_ref[e & ~kRefLeafTag]);
+						uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
 						all_a &= (ab.x == ta || ab.y == ta);
 						all_b &= (ab.x == tb || ab.y == tb);
 					}
@@ -423,7 +450,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 					const bool is_d = (e & kRefLeafTag) != 0;
 					const uint32_t leaf = e & ~kRefLeafTag;
 					if (MODE == CQ_MODE_P && accepted)
-						atomicAdd(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], 1u);
+						redAddStream(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], pol_stream);
 					if (want_sets) {
 						uint32_t at = is_d ? distinct_d : distinct_u;
 						if (at < p.leaf_cap)
