@@ -334,9 +334,11 @@ def main():
     gsec = ctx.bench_random_sectors(1 << 28, iters=2) if rank == 0 else 0.0
 
     # ---- (2) end to end through the C ABI with HOST buffers ------------------------------------
+    pinned_out = ctx.pinned_result_buffers()
+
     def step_e2e():
         ctx.reset()
-        r = ctx.query(mode, reads.reshape(-1), None, lengths, stride=rl)
+        r = ctx.query(mode, reads.reshape(-1), None, lengths, stride=rl, buffers=pinned_out)
         combine()
         return r
 

@@ -100,6 +100,8 @@ SYMBOLS = {
     "cq_query": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                            C.c_uint64, C.POINTER(Result)]),
     "cq_reset": (C.c_int, [C.c_void_p]),
+    "cq_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cq_host_free": (None, [C.c_void_p]),
     "cq_reads_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "cq_query_staged": (C.c_int, [C.c_void_p, C.c_int]),
     "cq_sync": (C.c_int, [C.c_void_p]),
@@ -215,6 +217,7 @@ class Context:
         _check(lib().cq_ctx_create(device, handle, C.byref(self._h)))
         self.n_genomes = 0
         self.index = None
+        self._pinned = []
 
     def upload(self, index, n_genomes):
         _check(lib().cq_index_upload(self._h, index._h, n_genomes))
@@ -224,15 +227,30 @@ class Context:
     def reset(self):
         _check(lib().cq_reset(self._h))
 
-    def _result(self, mode, n_reads, per_read, leaf_cap, want_rcount, pairs_cap):
+    def pinned_result_buffers(self):
+        """Reusable page-locked buffers for cnt_u/cnt_d/rcount_u/rcount_d (pass as `buffers=`)."""
+        G, idx = self.n_genomes, self.index
+        out = {}
+        for name, n, dt in (("cnt_u", G + 1, np.uint64), ("cnt_d", G + 1, np.uint64),
+                            ("rcount_u", max(idx.n_leaves_u, 1), np.uint32),
+                            ("rcount_d", max(idx.n_leaves_d, 1), np.uint32)):
+            p = C.c_void_p()
+            nbytes = n * np.dtype(dt).itemsize
+            _check(lib().cq_host_alloc(nbytes, C.byref(p)))
+            self._pinned.append(p)
+            out[name] = np.frombuffer((C.c_char * nbytes).from_address(p.value), dtype=dt)
+        return out
+
+    def _result(self, mode, n_reads, per_read, leaf_cap, want_rcount, pairs_cap, buffers=None):
         G, idx = self.n_genomes, self.index
         res, keep = Result(), {}
-        keep["cnt_u"] = np.zeros(G + 1, dtype=np.uint64)
-        keep["cnt_d"] = np.zeros(G + 1, dtype=np.uint64)
+        buffers = buffers or {}
+        keep["cnt_u"] = buffers["cnt_u"] if "cnt_u" in buffers else np.zeros(G + 1, dtype=np.uint64)
+        keep["cnt_d"] = buffers["cnt_d"] if "cnt_d" in buffers else np.zeros(G + 1, dtype=np.uint64)
         res.cnt_u, res.cnt_d = keep["cnt_u"].ctypes.data, keep["cnt_d"].ctypes.data
         if mode == MODE_P and want_rcount:
-            keep["rcount_u"] = np.zeros(max(idx.n_leaves_u, 1), dtype=np.uint32)
-            keep["rcount_d"] = np.zeros(max(idx.n_leaves_d, 1), dtype=np.uint32)
+            keep["rcount_u"] = buffers["rcount_u"] if "rcount_u" in buffers else np.zeros(max(idx.n_leaves_u, 1), dtype=np.uint32)
+            keep["rcount_d"] = buffers["rcount_d"] if "rcount_d" in buffers else np.zeros(max(idx.n_leaves_d, 1), dtype=np.uint32)
             res.rcount_u, res.rcount_d = keep["rcount_u"].ctypes.data, keep["rcount_d"].ctypes.data
         if mode == MODE_SC:
             keep["_pairs"] = (PairCount * pairs_cap)()
@@ -271,14 +289,14 @@ class Context:
         return out
 
     def query(self, mode, bases, offsets, lengths, stride=0, per_read=False, leaf_cap=0,
-              want_rcount=True, pairs_cap=1 << 16):
+              want_rcount=True, pairs_cap=1 << 16, buffers=None):
         """bases uint8[], offsets uint64[] or None (fixed stride), lengths uint8[] (host arrays)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
         if offsets is not None:
             offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(lengths)
-        res, keep = self._result(mode, n, per_read, leaf_cap, want_rcount, pairs_cap)
+        res, keep = self._result(mode, n, per_read, leaf_cap, want_rcount, pairs_cap, buffers)
         _check(lib().cq_query(self._h, mode, bases.ctypes.data,
                               offsets.ctypes.data if offsets is not None else None, stride,
                               lengths.ctypes.data, n, C.byref(res)))
@@ -349,6 +367,9 @@ class Context:
         if self._h:
             lib().cq_ctx_destroy(self._h)
             self._h = C.c_void_p()
+        for p in self._pinned:
+            lib().cq_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:

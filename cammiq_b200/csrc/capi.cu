@@ -76,6 +76,15 @@ struct cq_ctx {
 	uint64_t staged_reads = 0, staged_stride = 0, staged_bytes = 0;
 	bool staged_has_offsets = false;
 	uint32_t staged_max_len = 0;
+	size_t last_dyn_smem[4] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
+	int last_per_sm[4] = {0, 0, 0, 0};
+	// double-buffered host->device pipeline of cq_query
+	cudaStream_t copy_stream = NULL;
+	cudaEvent_t ev_copied[2] = {NULL, NULL}, ev_free[2] = {NULL, NULL};
+	uint8_t *d_cbases[2] = {NULL, NULL};
+	uint64_t *d_coffsets[2] = {NULL, NULL};
+	uint8_t *d_clengths[2] = {NULL, NULL};
+	size_t cap_cbases[2] = {0, 0}, cap_coffsets[2] = {0, 0}, cap_clengths[2] = {0, 0};
 	// SC pair records (device, grows)
 	unsigned long long *d_pairs = NULL;
 	size_t cap_pairs = 0;
@@ -265,8 +274,12 @@ extern "C" int cq_ctx_create(int device, void *stream, cq_ctx **out) {
 		}
 		c->own_stream = true;
 	}
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < 2; i++) {
 		cudaEventCreate(&c->ev[i]);
+		cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming);
+	}
+	cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
 	*out = c;
 	return CQ_OK;
 }
@@ -281,8 +294,13 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
 	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
 	cudaFree(c->d_leaf_d);
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < 2; i++) {
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+		if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+		cudaFree(c->d_cbases[i]); cudaFree(c->d_coffsets[i]); cudaFree(c->d_clengths[i]);
+	}
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	for (auto &se : c->steps)
 		for (int i = 0; i < 4; i++)
 			cudaEventDestroy(se.e[i]);
@@ -433,13 +451,95 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	return CQ_OK;
 }
 
-extern "C" int cq_query_staged(cq_ctx *c, int mode) {
-	if (c == NULL || !c->has_index)
-		return fail(CQ_ESTATE, "cq_query_staged: no index resident.");
-	if (mode != CQ_MODE_P && mode != CQ_MODE_SC)
-		return fail(CQ_EINVAL, "cq_query_staged: bad mode.");
-	CQ_CUDA(cudaSetDevice(c->device));
-	const uint64_t n = c->staged_reads;
+// One launch of the scan (+ partial-count reduction) over a batch of reads resident on the
+// device.  `bases` is the address read offset 0 would have (the batch may hold only a slice
+// of the caller's base buffer), `first` is the caller's index of the batch's first read.
+struct ReadBatch {
+	const uint8_t *bases;
+	const uint64_t *offsets;
+	uint64_t stride;
+	const uint8_t *lengths;
+	uint64_t n, first;
+	uint32_t max_len;
+};
+
+static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
+	if (rb.n == 0)
+		return CQ_OK;
+	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
+	ScanParams sp;
+	memset(&sp, 0, sizeof(sp));
+	sp.table = c->d_table;
+	sp.table_mask = c->table_mask;
+	sp.nodes_u = c->d_nodes_u;
+	sp.nodes_d = c->d_nodes_d;
+	sp.leaf_u_ref = c->d_leaf_u_ref;
+	sp.leaf_d_ref = c->d_leaf_d_ref;
+	sp.h = c->h;
+	sp.n_genomes = c->n_genomes;
+	sp.filter = c->d_filter;
+	sp.filter_mask = c->filter_mask;
+	sp.bases = rb.bases;
+	sp.offsets = rb.offsets;
+	sp.stride = rb.stride;
+	sp.read_base = rb.first;
+	sp.lengths = rb.lengths;
+	sp.n_reads = rb.n;
+	// shared-memory tile: the byte range 256 back-to-back reads of the longest length span
+	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
+	const uint32_t tile_cap = (kScanThreads * std::max<uint32_t>(rb.max_len, 1) + 32 + 127) & ~127u;
+	sp.tile_cap = tile_cap;
+	const size_t dyn_smem = tile_cap + c->smem_bytes;
+	sp.smem_counters = c->smem_counters ? 1 : 0;
+	sp.partials = c->d_partials;
+	sp.counts = c->d_counts;
+	sp.rcount_u = c->d_rcount_u;
+	sp.rcount_d = c->d_rcount_d;
+	sp.pair_records = c->d_pairs;
+	sp.hit_spill = c->d_spill;
+	sp.probe_count = c->d_probe_count;
+	if (c->want_per_read) {
+		sp.read_class = c->d_read_class + rb.first;
+		sp.read_rid_a = c->d_read_rid_a + rb.first;
+		sp.read_rid_b = c->d_read_rid_b + rb.first;
+	}
+	if (c->want_sets) {
+		sp.leaf_cap = c->leaf_cap;
+		sp.read_nleaf_u = c->d_nleaf_u + rb.first;
+		sp.read_nleaf_d = c->d_nleaf_d + rb.first;
+		sp.read_leaf_u = c->d_leaf_u + rb.first * c->leaf_cap;
+		sp.read_leaf_d = c->d_leaf_d + rb.first * c->leaf_cap;
+	}
+	const bool filt = c->d_filter != NULL;
+	const void *kern = mode == CQ_MODE_P
+		? (filt ? (const void *) scan_reads_kernel<CQ_MODE_P, true> : (const void *) scan_reads_kernel<CQ_MODE_P, false>)
+		: (filt ? (const void *) scan_reads_kernel<CQ_MODE_SC, true> : (const void *) scan_reads_kernel<CQ_MODE_SC, false>);
+	const int variant = mode * 2 + (filt ? 1 : 0);
+	if (dyn_smem != c->last_dyn_smem[variant]) {
+		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
+		int per_sm = 0;
+		CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScanThreads, dyn_smem));
+		if (per_sm < 1)
+			return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
+		c->last_dyn_smem[variant] = dyn_smem;
+		c->last_per_sm[variant] = std::min(per_sm, kMaxBlocksPerSM);
+	}
+	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads;
+	c->grid = (int) std::min<uint64_t>((uint64_t) c->last_per_sm[variant] * c->n_sms, n_tiles);
+	void *args[] = {&sp};
+	CQ_CUDA(cudaLaunchKernel(kern, dim3(c->grid), dim3(kScanThreads), args, dyn_smem, c->stream));
+	c->timing.kernel_launches++;
+	c->timing.scan_launches++;
+	if (c->smem_counters) {
+		reduce_partials_kernel<<<(unsigned) ((ncnt + 255) / 256), 256, 0, c->stream>>>(
+			c->d_partials, (uint32_t) c->grid, (uint32_t) ncnt, c->d_counts);
+		c->timing.kernel_launches++;
+	}
+	return CQ_OK;
+}
+
+// Device buffers a query of n reads needs besides the reads themselves.
+static int prepareOutputs(cq_ctx *c, int mode, uint64_t n) {
 	int rc;
 	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
 	if (mode == CQ_MODE_SC) {
@@ -460,8 +560,8 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		}
 	}
 	if (c->want_per_read) {
-		if ((rc = ensure(&c->d_read_class, &c->cap_per_read, (size_t) n)) != 0) return rc;
 		size_t cap2 = 0;
+		cap2 = 0; if ((rc = ensure(&c->d_read_class, &cap2, (size_t) n)) != 0) return rc;
 		cap2 = 0; if ((rc = ensure(&c->d_read_rid_a, &cap2, (size_t) n)) != 0) return rc;
 		cap2 = 0; if ((rc = ensure(&c->d_read_rid_b, &cap2, (size_t) n)) != 0) return rc;
 	}
@@ -474,7 +574,11 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 		CQ_CUDA(cudaMemsetAsync(c->d_leaf_u, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 		CQ_CUDA(cudaMemsetAsync(c->d_leaf_d, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 	}
+	return CQ_OK;
+}
 
+static int beginStep(cq_ctx *c, cudaEvent_t **sev) {
+	int rc;
 	if (c->steps_used == c->steps.size()) {
 		if (c->steps.size() >= 1024) {
 			if ((rc = foldStepEvents(c)) != 0) return rc;
@@ -485,75 +589,27 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 			c->steps.push_back(se);
 		}
 	}
-	cudaEvent_t *sev = c->steps[c->steps_used++].e;
+	*sev = c->steps[c->steps_used++].e;
 	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 32, c->stream));
+	return CQ_OK;
+}
+
+extern "C" int cq_query_staged(cq_ctx *c, int mode) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_query_staged: no index resident.");
+	if (mode != CQ_MODE_P && mode != CQ_MODE_SC)
+		return fail(CQ_EINVAL, "cq_query_staged: bad mode.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	int rc;
+	if ((rc = prepareOutputs(c, mode, c->staged_reads)) != 0) return rc;
+	cudaEvent_t *sev;
+	if ((rc = beginStep(c, &sev)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
-	if (n > 0) {
-		ScanParams sp;
-		memset(&sp, 0, sizeof(sp));
-		sp.table = c->d_table;
-		sp.table_mask = c->table_mask;
-		sp.nodes_u = c->d_nodes_u;
-		sp.nodes_d = c->d_nodes_d;
-		sp.leaf_u_ref = c->d_leaf_u_ref;
-		sp.leaf_d_ref = c->d_leaf_d_ref;
-		sp.h = c->h;
-		sp.n_genomes = c->n_genomes;
-		sp.filter = c->d_filter;
-		sp.filter_mask = c->filter_mask;
-		sp.bases = c->d_bases;
-		sp.offsets = c->staged_has_offsets ? c->d_offsets : NULL;
-		sp.stride = c->staged_stride;
-		sp.lengths = c->d_lengths;
-		sp.n_reads = n;
-		// shared-memory tile: the byte range 256 back-to-back reads of the longest length span
-		// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
-		const uint32_t tile_cap = (kScanThreads * std::max<uint32_t>(c->staged_max_len, 1) + 32 + 127) & ~127u;
-		sp.tile_cap = tile_cap;
-		const size_t dyn_smem = tile_cap + c->smem_bytes;
-		sp.smem_counters = c->smem_counters ? 1 : 0;
-		sp.partials = c->d_partials;
-		sp.counts = c->d_counts;
-		sp.rcount_u = c->d_rcount_u;
-		sp.rcount_d = c->d_rcount_d;
-		sp.pair_records = c->d_pairs;
-		sp.hit_spill = c->d_spill;
-		sp.probe_count = c->d_probe_count;
-		if (c->want_per_read) {
-			sp.read_class = c->d_read_class;
-			sp.read_rid_a = c->d_read_rid_a;
-			sp.read_rid_b = c->d_read_rid_b;
-		}
-		if (c->want_sets) {
-			sp.leaf_cap = c->leaf_cap;
-			sp.read_nleaf_u = c->d_nleaf_u;
-			sp.read_nleaf_d = c->d_nleaf_d;
-			sp.read_leaf_u = c->d_leaf_u;
-			sp.read_leaf_d = c->d_leaf_d;
-		}
-		const bool filt = c->d_filter != NULL;
-		const void *kern = mode == CQ_MODE_P
-			? (filt ? (const void *) scan_reads_kernel<CQ_MODE_P, true> : (const void *) scan_reads_kernel<CQ_MODE_P, false>)
-			: (filt ? (const void *) scan_reads_kernel<CQ_MODE_SC, true> : (const void *) scan_reads_kernel<CQ_MODE_SC, false>);
-		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
-		int per_sm = 0;
-		CQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScanThreads, dyn_smem));
-		if (per_sm < 1)
-			return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
-		const uint64_t n_tiles = (n + kScanThreads - 1) / kScanThreads;
-		c->grid = (int) std::min<uint64_t>((uint64_t) std::min(per_sm, kMaxBlocksPerSM) * c->n_sms, n_tiles);
-		void *args[] = {&sp};
-		CQ_CUDA(cudaLaunchKernel(kern, dim3(c->grid), dim3(kScanThreads), args, dyn_smem, c->stream));
-		c->timing.kernel_launches++;
-		c->timing.scan_launches++;
-	}
+	ReadBatch rb = {c->d_bases, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
+		c->staged_reads, 0, c->staged_max_len};
+	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
-	if (n > 0 && c->smem_counters) {
-		reduce_partials_kernel<<<(unsigned) ((ncnt + 255) / 256), 256, 0, c->stream>>>(
-			c->d_partials, (uint32_t) c->grid, (uint32_t) ncnt, c->d_counts);
-		c->timing.kernel_launches++;
-	}
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
 	CQ_CUDA(cudaGetLastError());
 	return CQ_OK;
@@ -634,21 +690,79 @@ static int fetchPerRead(cq_ctx *c, uint64_t n, cq_result *out) {
 	return CQ_OK;
 }
 
+static const uint64_t kChunkReads = 1u << 20; // reads per pipeline stage of cq_query
+
 extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
 	if (c == NULL || !c->has_index)
 		return fail(CQ_ESTATE, "cq_query: no index resident (call cq_index_upload first).");
-	if (out == NULL)
-		return fail(CQ_EINVAL, "cq_query: NULL result.");
+	if (out == NULL || (mode != CQ_MODE_P && mode != CQ_MODE_SC))
+		return fail(CQ_EINVAL, "cq_query: NULL result or bad mode.");
+	if (n_reads > 0 && (bases == NULL || lengths == NULL))
+		return fail(CQ_EINVAL, "cq_query: NULL read buffers.");
+	CQ_CUDA(cudaSetDevice(c->device));
 	auto t0 = std::chrono::high_resolution_clock::now();
 	c->want_per_read = out->read_class != NULL && out->read_rid_a != NULL && out->read_rid_b != NULL;
 	c->want_sets = out->leaf_cap > 0 && out->read_nleaf_u && out->read_nleaf_d && out->read_leaf_u && out->read_leaf_d;
 	c->leaf_cap = c->want_sets ? out->leaf_cap : 0;
-	int rc = cq_reads_stage(c, bases, offsets, stride, lengths, n_reads);
-	if (rc == 0) rc = cq_query_staged(c, mode);
-	if (rc == 0) rc = cq_sync(c);
+	int rc = prepareOutputs(c, mode, n_reads);
+	cudaEvent_t *sev = NULL;
+	if (rc == 0) rc = beginStep(c, &sev);
+	if (rc != 0) return rc;
+	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
+	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
+	CQ_CUDA(cudaEventRecord(c->ev[0], c->stream));
+	// Chunks of reads flow host -> device on the copy stream while the previous chunk is
+	// scanned on the compute stream (two staging buffers).
+	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
+		const int b = (int) (k & 1);
+		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
+		uint64_t lo = ~0ull, hi = 0;
+		uint32_t max_len = 1;
+		if (offsets) {
+			for (uint64_t i = first; i < first + n; i++) {
+				lo = std::min(lo, offsets[i]);
+				hi = std::max(hi, offsets[i] + lengths[i]);
+				max_len = std::max<uint32_t>(max_len, lengths[i]);
+			}
+		} else {
+			for (uint64_t i = first; i < first + n; i++)
+				max_len = std::max<uint32_t>(max_len, lengths[i]);
+			// fixed stride: only the reads within 255 bytes of the chunk's end can set its extent
+			lo = first * stride;
+			hi = lo;
+			for (uint64_t i = first + n; i-- > first;) {
+				hi = std::max(hi, i * stride + lengths[i]);
+				if ((first + n - 1 - i) * stride >= 255)
+					break;
+			}
+		}
+		if (hi < lo) hi = lo;
+		const uint64_t copy_lo = lo & ~15ull, copy_bytes = hi - copy_lo;
+		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], copy_bytes + 32)) != 0) return rc;
+		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], n)) != 0) return rc;
+		if (offsets && (rc = ensure(&c->d_coffsets[b], &c->cap_coffsets[b], n)) != 0) return rc;
+		if (k >= 2)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+		else if (k == 0)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0)); // after earlier work on the compute stream
+		if (copy_bytes > 0)
+			CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], bases + copy_lo, copy_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+		CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], lengths + first, n, cudaMemcpyHostToDevice, c->copy_stream));
+		if (offsets)
+			CQ_CUDA(cudaMemcpyAsync(c->d_coffsets[b], offsets + first, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+		ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len};
+		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
+		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
+	}
+	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
+	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
+	CQ_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	CQ_CUDA(cudaGetLastError());
 	auto t1 = std::chrono::high_resolution_clock::now();
-	if (rc == 0) rc = cq_fetch(c, mode, out);
+	rc = cq_fetch(c, mode, out);
 	if (rc == 0) rc = fetchPerRead(c, n_reads, out);
 	c->want_per_read = c->want_sets = false;
 	c->leaf_cap = 0;
@@ -656,6 +770,22 @@ extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_
 	c->timing.d2h_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
 	c->timing.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
 	return rc;
+}
+
+extern "C" int cq_host_alloc(size_t bytes, void **out) {
+	if (out == NULL)
+		return fail(CQ_EINVAL, "cq_host_alloc: NULL argument.");
+	*out = NULL;
+	cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault);
+	if (e != cudaSuccess)
+		return fail(e == cudaErrorMemoryAllocation ? CQ_ENOMEM : CQ_ENODEV,
+			std::string("cq_host_alloc: ") + cudaGetErrorString(e));
+	return CQ_OK;
+}
+
+extern "C" void cq_host_free(void *p) {
+	if (p != NULL)
+		cudaFreeHost(p);
 }
 
 extern "C" int cq_get_device_counters(cq_ctx *c, cq_device_counters *out) {

@@ -51,8 +51,9 @@ struct ScanParams {
 	uint32_t n_genomes;
 	// reads: ASCII in device memory, exactly the state query64_* consumes
 	const uint8_t *bases;
-	const uint64_t *offsets;  // NULL: read i starts at i*stride
+	const uint64_t *offsets;  // NULL: read i starts at (read_base + i)*stride
 	uint64_t stride;
+	uint64_t read_base;       // caller's index of this launch's first read (chunked submission)
 	const uint8_t *lengths;
 	uint64_t n_reads;
 	uint32_t tile_cap;        // bytes of shared memory reserved for the ASCII tile
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 	for (uint64_t tile_idx = blockIdx.x; tile_idx < n_tiles; tile_idx += gridDim.x) {
 		const uint64_t r = tile_idx * kScanThreads + tid;
 		const bool have = r < p.n_reads;
-		const uint64_t off = have ? (p.offsets ? p.offsets[r] : r * p.stride) : ~0ull;
+		const uint64_t off = have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
 		uint32_t rl = have ? p.lengths[r] : 0;
 
 		// ---- stage the tile: one TMA bulk copy of the byte range the 256 reads span -------------

@@ -194,6 +194,11 @@ int cq_query(cq_ctx *ctx, int mode, const uint8_t *bases, const uint64_t *offset
 /* Zero the accumulated counters (cnt_u/d, rcount, nundet, nconf, n_invalid, pairs). */
 int cq_reset(cq_ctx *ctx);
 
+/* Page-locked host memory for read and result buffers: cq_query's host<->device copies run
+   asynchronously (and overlap the scan) only from pinned memory. */
+int cq_host_alloc(size_t bytes, void **out);
+void cq_host_free(void *p);
+
 /* ------------------------------------------- device-resident entry points (plumbing) -- */
 /*
  * For callers that keep reads in HBM and combine counters themselves (bench.py, the

@@ -160,3 +160,52 @@ def test_dense_index_spills_hit_list(ctx, tmp_path):
                 assert want["rcount_u"].sum() > 0
             else:
                 assert got["pairs"] == want["pairs"]
+
+
+def test_chunked_pipeline_matches_single_launch_and_oracle(ctx, tmp_path):
+    """cq_query streams reads in 2^20-read chunks through two staging buffers; the result must
+    equal the single-launch device-resident path, and per-read records around the chunk
+    boundaries must equal the oracle (fixed-stride and offsets addressing, ragged lengths)."""
+    from cammiq_b200 import synthlib as sl
+    p = sl.params(seed=7, n_genomes=12, genome_len=200_000, cluster_size=3)
+    sl.write_index(p, str(tmp_path))
+    iu, idd = str(tmp_path / "index_u.bin1"), str(tmp_path / "index_d.bin2")
+    idx = cq.Index(iu, idd)
+    ctx.upload(idx, 12)
+    n, rl = (1 << 21) + 12345, 100
+    reads = sl.make_reads(p, 0, n, rl, 0.01)
+    rng = np.random.default_rng(1)
+    lengths = rng.integers(60, rl + 1, size=n).astype(np.uint8)
+    lengths[::1000] = 10           # shorter than h
+    reads[5::7777, 50] = ord("N")  # invalid byte
+    flat = reads.reshape(-1)
+    # (a) fixed stride, chunked host path vs device-resident single launch
+    a = ctx.query(cq.MODE_P, flat, None, lengths, stride=rl, per_read=True)
+    ctx.reset()
+    ctx.stage(flat, None, lengths, stride=rl)
+    ctx.query_staged(cq.MODE_P)
+    b = ctx.fetch(cq.MODE_P)
+    for k in ("cnt_u", "cnt_d", "rcount_u", "rcount_d"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["nundet"], a["nconf"], a["n_invalid"]) == (b["nundet"], b["nconf"], b["n_invalid"])
+    assert a["n_invalid"] == len(range(0, n, 1000)) + len(set(range(5, n, 7777)) - set(range(0, n, 1000)))
+    # (b) offsets addressing (reads stored back to back, ragged), chunked
+    offsets = np.zeros(n, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths.astype(np.uint64))[:-1]
+    ragged = np.concatenate([reads[i, :lengths[i]] for i in range(0, n, 1)]) if n < 1000 else None
+    if ragged is None:
+        mask = np.arange(rl)[None, :] < lengths[:, None]
+        ragged = reads[mask]
+    ctx.reset()
+    c2 = ctx.query(cq.MODE_P, ragged, offsets, lengths, per_read=True)
+    for k in ("cnt_u", "cnt_d", "rcount_u", "rcount_d", "read_class", "read_rid_a", "read_rid_b"):
+        assert np.array_equal(a[k], c2[k]), k
+    # (c) oracle on windows around the chunk boundaries
+    ou, od = ol.OracleIndex(iu), ol.OracleIndex(idd)
+    for lo in (0, (1 << 20) - 1500, (1 << 21) - 1500, n - 3000):
+        hi = min(lo + 3000, n)
+        want = ol.oracle_query(ou, od, ol.MODE_P, 12, flat, np.arange(lo, hi, dtype=np.uint64) * rl,
+                               lengths[lo:hi], per_read=True)
+        for k in ("read_class", "read_rid_a", "read_rid_b"):
+            assert np.array_equal(a[k][lo:hi], want[k]), (k, lo)
+    assert (a["read_class"] >= 2).sum() > n // 10
