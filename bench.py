@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--workdir", default=os.environ.get("CAMMIQ_BENCH_DIR", "/tmp"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="p", choices=["p", "sc"])
+    ap.add_argument("--filter-mb", type=float, default=-1, help="override the membership-filter budget (MB, 0 = none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cammiq" else max(args.warmup, 1)
     name = args.workload
@@ -243,6 +244,8 @@ def main():
         dist.barrier()
     d = workdir_for(name, w, args.workdir)
     idx = cq.Index(os.path.join(d, "index_u.bin1"), os.path.join(d, "index_d.bin2"))
+    if args.filter_mb >= 0:
+        idx.set_filter_budget(int(args.filter_mb * (1 << 20)))
     info = idx.info
     # everything (kernels, memsets, NCCL hand-off, the timing events) runs on one torch stream
     torch.cuda.set_stream(torch.cuda.Stream())
@@ -389,6 +392,7 @@ def main():
                        "hash_len": h, "mode": "query64_p" if mode == cq.MODE_P else "query64_sc",
                        "leaves_u": info.n_leaves_u, "leaves_d": info.n_leaves_d,
                        "table_gb": info.n_table_buckets * 32 / 1e9, "index_device_gb": info.device_bytes / 1e9,
+                       "filter_mb": info.filter_bytes / (1 << 20),
                        "l2_policy": "inputs larger than L2: %.2f GB prefix table + %.2f GB reads per step" % (
                            info.n_table_buckets * 32 / 1e9, n * rl / 1e9),
                        "parallelism": "index replicated, reads sharded, 1 NCCL reduce/step" if world > 1 else "1 GPU",

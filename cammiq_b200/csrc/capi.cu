@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -62,7 +63,7 @@ struct cq_ctx {
 	uint32_t *d_partials = NULL;
 	uint32_t *d_spill = NULL; // per-read hit overflow, [max grid warps][32][kHitSpill]
 	uint2 *d_filter = NULL;
-	uint64_t filter_mask = 0;
+	uint32_t filter_shift = 0;
 	int max_grid = 0;
 	unsigned long long *d_probe_count = NULL;
 	int grid = 0;
@@ -353,7 +354,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 
 	if (!f.filter.empty()) {
 		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), c->stream)) != 0) return rc;
-		c->filter_mask = f.filter.size() - 1;
+		c->filter_shift = f.filter_shift;
 		CQ_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	// block-private genome counters in shared memory when they fit, global atomics otherwise;
@@ -478,18 +479,22 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.h = c->h;
 	sp.n_genomes = c->n_genomes;
 	sp.filter = c->d_filter;
-	sp.filter_mask = c->filter_mask;
+	sp.filter_shift = c->filter_shift;
 	sp.bases = rb.bases;
 	sp.offsets = rb.offsets;
 	sp.stride = rb.stride;
 	sp.read_base = rb.first;
 	sp.lengths = rb.lengths;
 	sp.n_reads = rb.n;
-	// shared-memory tile: the byte range 256 back-to-back reads of the longest length span
+	// staging buffer: the byte range 32 back-to-back reads of the longest length span
 	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
-	const uint32_t tile_cap = (kScanThreads * std::max<uint32_t>(rb.max_len, 1) + 32 + 127) & ~127u;
+	const uint32_t tile_cap = (32 * std::max<uint32_t>(rb.max_len, 1) + 32 + 127) & ~127u;
 	sp.tile_cap = tile_cap;
-	const size_t dyn_smem = tile_cap + c->smem_bytes;
+	{
+		const char *dbg = getenv("CAMMIQ_DEBUG_FLAGS");
+		sp.debug_flags = dbg ? (uint32_t) atoi(dbg) : 0u;
+	}
+	const size_t dyn_smem = (size_t) kWarpsPerBlock * tile_cap + c->smem_bytes;
 	sp.smem_counters = c->smem_counters ? 1 : 0;
 	sp.partials = c->d_partials;
 	sp.counts = c->d_counts;
@@ -524,7 +529,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 		c->last_dyn_smem[variant] = dyn_smem;
 		c->last_per_sm[variant] = std::min(per_sm, kMaxBlocksPerSM);
 	}
-	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads;
+	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads; // one 32-read sub-tile per warp at least
 	c->grid = (int) std::min<uint64_t>((uint64_t) c->last_per_sm[variant] * c->n_sms, n_tiles);
 	void *args[] = {&sp};
 	CQ_CUDA(cudaLaunchKernel(kern, dim3(c->grid), dim3(kScanThreads), args, dyn_smem, c->stream));

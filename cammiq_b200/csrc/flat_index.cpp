@@ -93,19 +93,21 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 		return;
 	// 16 bits per key when they fit, never fewer than kFilterMinBitsPerKey
 	uint64_t words = 1024;
-	while (words * 64 < fi.n_keys * 16 && words * 8 * 2 <= max_bytes)
+	while (words * 64 < fi.n_keys * 16 && words * 8 * 2 <= max_bytes && words < (1ull << 31))
 		words <<= 1;
 	if (words * 64 < fi.n_keys * kFilterMinBitsPerKey)
 		return; // would not fit L2 at a useful false-positive rate: probe the table directly
 	fi.filter.assign(words, 0);
-	const uint64_t wmask = words - 1;
+	uint32_t bits = 0;
+	while ((1ull << bits) < words)
+		bits++;
+	fi.filter_shift = 32 - bits;
 	for (size_t i = 0; i < fi.table.size(); i++) {
 		if (fi.table[i].key == kEmptyKey)
 			continue;
-		uint64_t w;
-		uint32_t lo, hi;
-		filterProbe(mixKey(fi.table[i].key), wmask, w, lo, hi);
-		fi.filter[w] |= (uint64_t) lo | ((uint64_t) hi << 32);
+		uint32_t A, B;
+		filterHash(fi.table[i].key, A, B);
+		fi.filter[filterWordIndex(A, fi.filter_shift)] |= filterMask(B);
 	}
 }
 
@@ -113,11 +115,10 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 	uint64_t mask = fi.n_table_buckets - 1;
 	if (!fi.filter.empty()) {
 		// same gate as phase 1 of the scan kernel: a filter miss ends the lookup
-		uint64_t w;
-		uint32_t lo, hi;
-		filterProbe(mixKey(bucket), fi.filter.size() - 1, w, lo, hi);
-		uint64_t m = (uint64_t) lo | ((uint64_t) hi << 32);
-		if ((fi.filter[w] & m) != m)
+		uint32_t A, B;
+		filterHash(bucket, A, B);
+		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_shift)];
+		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
 			return UINT64_MAX;
 	}
 	uint64_t b = mixKey(bucket) & mask;

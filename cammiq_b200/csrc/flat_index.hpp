@@ -44,22 +44,43 @@ inline uint64_t mixKey(uint64_t x) {
 }
 
 // L2-resident membership filter in front of the table: register-blocked Bloom filter, one
-// 64-bit word per key (two bits in each 32-bit half).  ~98-99% of probes miss (SURVEY.md
+// 64-bit word per key, two bits in each 32-bit half.  ~98-99% of probes miss (SURVEY.md
 // Appendix A.6); a filter that fits the B200's L2 (random gathers over <= 64 MB run at
 // ~285 G/s versus ~45 G sectors/s from HBM, profiles/r01_microbench_gather.json) answers
-// them without touching DRAM.  Word index = bits 32.. of mixKey, bit selectors = its low 20
-// bits (independent of the word index).
+// them without touching DRAM.  The filter hash is deliberately lean (6 integer multiplies,
+// 32-bit only): it runs twice per read position.  Word index = top bits of A, bit
+// selectors = top 20 bits of B; (f, g) keep the 62-bit key injective before mixing.
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
-static const uint32_t kFilterMinBitsPerKey = 8;
+static const uint32_t kFilterMinBitsPerKey = 3;
 
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline void filterProbe(uint64_t mixed, uint64_t word_mask, uint64_t &word, uint32_t &mask_lo, uint32_t &mask_hi) {
-	word = (mixed >> 32) & word_mask;
-	uint32_t m = (uint32_t) mixed;
-	mask_lo = (1u << (m & 31)) | (1u << ((m >> 5) & 31));
-	mask_hi = (1u << ((m >> 10) & 31)) | (1u << ((m >> 15) & 31));
+inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
+	uint32_t lo = (uint32_t) key, hi = (uint32_t) (key >> 32);
+	uint32_t f = lo ^ (hi * 0x9E3779B1u);
+	uint32_t g = hi ^ (lo * 0x85EBCA77u);
+	A = f * 0xC2B2AE3Du;
+	A ^= A >> 15;
+	A *= 0x27D4EB2Fu;
+	B = (g ^ A) * 0x165667B1u;
+}
+// word index for a filter of 2^(32 - shift) words
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t filterWordIndex(uint32_t A, uint32_t shift) { return A >> shift; }
+// all four selected bits set in the word (x = low half, y = high half)?
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline bool filterTest(uint32_t x, uint32_t y, uint32_t B) {
+	return ((x >> (B >> 27)) & (x >> ((B >> 22) & 31u)) & (y >> ((B >> 17) & 31u)) & (y >> ((B >> 12) & 31u)) & 1u) != 0;
+}
+inline uint64_t filterMask(uint32_t B) {
+	uint32_t lo = (1u << (B >> 27)) | (1u << ((B >> 22) & 31u));
+	uint32_t hi = (1u << ((B >> 17) & 31u)) | (1u << ((B >> 12) & 31u));
+	return (uint64_t) lo | ((uint64_t) hi << 32);
 }
 
 struct FlatIndex {
@@ -68,6 +89,7 @@ struct FlatIndex {
 	uint64_t n_keys = 0;
 	std::vector<TableSlot> table; // n_table_buckets * kSlotsPerBucket
 	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
+	uint32_t filter_shift = 0;    // 32 - log2(filter words)
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
 	double decode_ms = 0, flatten_ms = 0;
 

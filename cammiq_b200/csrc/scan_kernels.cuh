@@ -28,7 +28,7 @@
 
 namespace cammiq {
 
-static const int kScanThreads = 256;          // = reads per tile
+static const int kScanThreads = 256;          // 8 warps, each streaming its own 32-read sub-tiles
 static const int kWarpsPerBlock = kScanThreads / 32;
 static const int kQueueCap = 512;             // per-warp candidate queue (drained when > 256 used)
 static const int kHitSeg = 8;                 // per-read hit slots in shared memory
@@ -43,7 +43,7 @@ struct ScanParams {
 	const TableSlot *table;
 	uint64_t table_mask;
 	const uint2 *filter;      // NULL: no filter, phase 1 probes the table
-	uint64_t filter_mask;     // words - 1
+	uint32_t filter_shift;    // 32 - log2(filter words)
 	const uint32_t *nodes_u, *nodes_d;
 	const uint32_t *leaf_u_ref;
 	const uint2 *leaf_d_ref;
@@ -56,7 +56,8 @@ struct ScanParams {
 	uint64_t read_base;       // caller's index of this launch's first read (chunked submission)
 	const uint8_t *lengths;
 	uint64_t n_reads;
-	uint32_t tile_cap;        // bytes of shared memory reserved for the ASCII tile
+	uint32_t tile_cap;        // bytes of one staging buffer (32 reads); 2 per warp
+	uint32_t debug_flags;     // experiments only (CAMMIQ_DEBUG_FLAGS): 1 plain filter loads, 2 skip phases 2+3, 4 no filter loads
 	// outputs
 	int smem_counters;        // 1: block-private genome counters + partials, 0: global atomics
 	uint32_t *partials;       // [gridDim.x][2*(G+1)]
@@ -149,13 +150,21 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
 }
 
 struct WarpState {
-	uint32_t queue[kQueueCap];     // slot<<16 | strand<<15 | position
-	uint32_t hits[32][kHitSeg];    // table<<31 | leaf id
-	const uint8_t *sptr[32];       // first base of the slot's read (shared or global)
-	uint32_t hit_cnt[32];
-	uint32_t rl[32];
+	uint32_t hits[32][kHitSeg];    // table<<31 | leaf id, per read of the warp's sub-tile
+	uint16_t queue[kQueueCap];     // slot<<9 | strand<<8 | position
+	uint32_t soff[32];             // byte offset of the slot's read inside the staged sub-tile
+	unsigned long long goff[32];   // its offset in the caller's base buffer (fallback path)
+	uint16_t hit_cnt[32];
+	uint8_t rl[32];
 	uint32_t q_count;
+	uint32_t staged;               // sub-tile is in shared memory (else: read from global)
+	uint64_t bar;                  // mbarrier of the warp's staging buffer
 };
+
+// first base of a slot's read, generic address space (phase 2 / trie descent only)
+__device__ __forceinline__ const uint8_t *slotBases(const ScanParams &p, const WarpState &ws, const uint8_t *buf, uint32_t slot) {
+	return ws.staged ? buf + ws.soff[slot] : p.bases + ws.goff[slot];
+}
 
 // base `j` of strand `strand` of a read (strand 1 = reverse complement, query.cpp:447-450)
 __device__ __forceinline__ uint32_t strandBase(const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t j) {
@@ -179,8 +188,8 @@ __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__rest
 
 // Phase 2: the warp drains its candidate queue.  One candidate per lane: recompute the h-mer,
 // probe the prefix table (HBM), descend, append leaves to the owning read's hit list.
-__device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, uint32_t *warp_spill, int lane,
-		uint32_t &n_leaf_hits, uint32_t &n_chained) {
+__device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, const uint8_t *buf, uint32_t *warp_spill,
+		int lane, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
 	const uint32_t nq = ws.q_count;
 	const uint32_t h = p.h;
@@ -188,8 +197,8 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 		const uint32_t k = base + lane;
 		if (k < nq) {
 			const uint32_t item = ws.queue[k];
-			const uint32_t slot = item >> 16, strand = (item >> 15) & 1u, pos = item & 0x7FFFu;
-			const uint8_t *s = ws.sptr[slot];
+			const uint32_t slot = item >> 9, strand = (item >> 8) & 1u, pos = item & 0xFFu;
+			const uint8_t *s = slotBases(p, ws, buf, slot);
 			const uint32_t rl = ws.rl[slot];
 			unsigned long long hv = 0;
 			for (uint32_t t = 0; t < h; t++)
@@ -216,7 +225,10 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 						continue;
 					n_leaf_hits++;
 					uint32_t e = (leaf[t] & ~kRefLeafTag) | (t ? kRefLeafTag : 0u);
-					uint32_t at = atomicAdd(&ws.hit_cnt[slot], 1u);
+					// 16-bit shared counter bumped through its containing 32-bit word
+					uint32_t *word = reinterpret_cast<uint32_t *>(&ws.hit_cnt[slot & ~1u]);
+					uint32_t old = atomicAdd(word, (slot & 1u) ? 0x10000u : 1u);
+					uint32_t at = (slot & 1u) ? (old >> 16) : (old & 0xFFFFu);
 					if (at < (uint32_t) kHitSeg) ws.hits[slot][at] = e;
 					else if (at < (uint32_t) (kHitSeg + kHitSpill)) warp_spill[(size_t) slot * kHitSpill + at - kHitSeg] = e;
 				}
@@ -229,161 +241,220 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 	__syncwarp();
 }
 
-template <int MODE, bool FILTER>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams p) {
-	extern __shared__ __align__(128) uint8_t dyn_smem[]; // [tile_cap ASCII tile][2*(G+1) u32 counters]
-	__shared__ WarpState warp_state[kWarpsPerBlock];
-	__shared__ __align__(8) uint64_t tile_bar;
-	__shared__ unsigned long long block_tot[2]; // nundet, nconf
-	__shared__ unsigned long long span_lo[kWarpsPerBlock], span_hi[kWarpsPerBlock];
+__device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
 
-	uint8_t *tile = dyn_smem;
-	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + p.tile_cap);
+template <int MODE, bool FILTER>
+__global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams p) {
+	// [8 warps][tile_cap bytes of ASCII] | [2*(G+1) u32 genome counters]
+	extern __shared__ __align__(128) uint8_t dyn_smem[];
+	__shared__ __align__(16) WarpState warp_state[kWarpsPerBlock];
+	__shared__ unsigned long long block_tot[2]; // nundet, nconf
+
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * p.tile_cap);
 	const uint32_t G1 = p.n_genomes + 1, ncnt = 2 * G1;
 	if (p.smem_counters)
 		for (uint32_t i = tid; i < ncnt; i += blockDim.x)
 			smem_counts[i] = 0;
 	if (tid < 2)
 		block_tot[tid] = 0;
-	if (tid == 0)
-		mbarInit(&tile_bar, 1);
 	WarpState &ws = warp_state[wib];
-	if (lane == 0)
+	if (lane == 0) {
 		ws.q_count = 0;
+		mbarInit(&ws.bar, 1);
+	}
 	__syncthreads();
 
 	const uint32_t h = p.h;
 	const unsigned long long pol_keep = policyEvictLast(), pol_stream = policyEvictFirst();
 	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
 	const uint32_t top_shift = 2 * h - 2;
+	uint8_t *wbuf = dyn_smem + (size_t) wib * p.tile_cap;
 	uint32_t *warp_spill = p.hit_spill + ((size_t) blockIdx.x * kWarpsPerBlock + wib) * 32 * kHitSpill;
 	unsigned long long n_undet = 0, n_conf = 0, n_invalid = 0;
 	uint32_t n_probes = 0, n_cand = 0, n_leaf_hits = 0, n_chained = 0; // per lane
-	uint32_t bar_parity = 0;
-	const uint64_t n_tiles = (p.n_reads + kScanThreads - 1) / kScanThreads;
+	uint32_t parity = 0;
 
-	for (uint64_t tile_idx = blockIdx.x; tile_idx < n_tiles; tile_idx += gridDim.x) {
-		const uint64_t r = tile_idx * kScanThreads + tid;
-		const bool have = r < p.n_reads;
-		const uint64_t off = have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
-		uint32_t rl = have ? p.lengths[r] : 0;
+	// Every warp owns sub-tiles of 32 reads (one read per lane) and streams them through its own
+	// staging buffer with its own mbarrier: no block-wide barrier in the loop, the other warps
+	// of the SM cover the (short) bulk-copy latency.
+	const uint64_t n_sub = (p.n_reads + 31) / 32;
+	const uint64_t warp_stride = (uint64_t) gridDim.x * kWarpsPerBlock;
+	uint64_t sub = (uint64_t) blockIdx.x * kWarpsPerBlock + wib;
 
-		// ---- stage the tile: one TMA bulk copy of the byte range the 256 reads span -------------
-		unsigned long long lo = have ? off : ~0ull, hi = have ? off + rl : 0ull;
+	struct SubTile {
+		unsigned long long off, start; // this lane's read offset; 16-byte aligned start of the span
+		uint32_t rl, bytes;
+		bool have, staged;
+	};
+	// offsets / lengths of a sub-tile's reads and the byte span they cover (warp-uniform)
+	auto describe = [&](uint64_t sub_idx) -> SubTile {
+		SubTile t;
+		const uint64_t r = sub_idx * 32 + lane;
+		t.have = r < p.n_reads;
+		t.off = t.have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
+		t.rl = t.have ? p.lengths[r] : 0;
+		unsigned long long lo = t.off, hi = t.have ? t.off + t.rl : 0ull;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			unsigned long long tl = __shfl_xor_sync(0xffffffffu, lo, o), th = __shfl_xor_sync(0xffffffffu, hi, o);
 			lo = tl < lo ? tl : lo;
 			hi = th > hi ? th : hi;
 		}
-		if (lane == 0) {
-			span_lo[wib] = lo;
-			span_hi[wib] = hi;
-		}
-		__syncthreads(); // also: every thread is done with the previous tile
-		lo = span_lo[0];
-		hi = span_hi[0];
-#pragma unroll
-		for (int w = 1; w < kWarpsPerBlock; w++) {
-			lo = span_lo[w] < lo ? span_lo[w] : lo;
-			hi = span_hi[w] > hi ? span_hi[w] : hi;
-		}
-		const unsigned long long start = lo & ~15ull;
-		const unsigned long long bytes = hi > start ? ((hi - start + 15ull) & ~15ull) : 0ull;
-		const bool staged = bytes > 0 && bytes <= p.tile_cap; // else: reads are fetched from global directly
-		if (staged) {
-			if (tid == 0) {
-				mbarExpectTx(&tile_bar, (uint32_t) bytes);
-				bulkCopyG2S(tile, p.bases + start, (uint32_t) bytes, &tile_bar, pol_stream);
+		t.start = lo & ~15ull;
+		t.bytes = hi > t.start ? (uint32_t) min((hi - t.start + 15ull) & ~15ull, 0xFFFFFFF0ull) : 0u;
+		t.staged = t.bytes > 0 && t.bytes <= p.tile_cap; // else: the reads are fetched from global directly
+		return t;
+	};
+
+	SubTile cur;
+	cur.have = false; cur.staged = false; cur.rl = 0; cur.off = 0; cur.start = 0; cur.bytes = 0;
+	if (sub < n_sub)
+		cur = describe(sub);
+	for (; sub < n_sub; sub += warp_stride) {
+		// one TMA bulk copy brings the sub-tile's ASCII bytes into the warp's buffer
+		if (cur.staged) {
+			if (lane == 0) {
+				mbarExpectTx(&ws.bar, cur.bytes);
+				bulkCopyG2S(wbuf, p.bases + cur.start, cur.bytes, &ws.bar, pol_stream);
 			}
-			mbarWait(&tile_bar, bar_parity);
-			bar_parity ^= 1u;
 		}
-		__syncthreads(); // span_lo/hi may be rewritten by the next iteration only after all read them
-		const uint8_t *s = have ? (staged ? tile + (off - start) : p.bases + off) : tile;
-		ws.sptr[lane] = s;
-		ws.rl[lane] = rl;
+		// the next sub-tile's offsets / lengths are fetched while this one is in flight
+		SubTile nxt;
+		nxt.have = false; nxt.staged = false; nxt.rl = 0; nxt.off = 0; nxt.start = 0; nxt.bytes = 0;
+		if (sub + warp_stride < n_sub)
+			nxt = describe(sub + warp_stride);
+		if (cur.staged) {
+			mbarWait(&ws.bar, parity);
+			parity ^= 1u;
+		}
+		const uint64_t r = sub * 32 + lane;
+		const bool have = cur.have, staged = cur.staged;
+		const uint32_t rl = cur.rl;
+		const uint8_t *tbuf = wbuf;
+		const uint32_t soff = staged && have ? (uint32_t) (cur.off - cur.start) : 0u;
+		ws.soff[lane] = soff;
+		ws.goff[lane] = have ? cur.off : 0ull;
+		ws.rl[lane] = (uint8_t) rl;
 		ws.hit_cnt[lane] = 0;
+		if (lane == 0)
+			ws.staged = staged ? 1u : 0u;
 		__syncwarp();
 
 		// ---- phase 1: thread per read, rolling hashes of both strands, filter / table test ------
-		bool bad = false;
+		// Four bases per iteration: one (unaligned) 32-bit shared load, SIMD-in-register decode
+		// and validation, then four roll steps; positions with a full h-base window are probed.
+		const uint32_t sbase = smemAddr(tbuf) + soff;
+		const uint8_t *gbase = p.bases + (have ? cur.off : 0ull);
+		uint32_t bad4 = 0;
 		unsigned long long hf = 0, hr = 0;
 		const uint32_t wmax = __reduce_max_sync(0xffffffffu, rl);
-		for (uint32_t j = 0; j + 1 < h; j++) {
-			if (j < rl) {
-				uint32_t c = decodeBase(s[j], bad);
-				hf = (hf << 2) | c;
-				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
+		for (uint32_t j0 = 0; j0 < wmax; j0 += kStepUnroll) {
+			// bytes j0..j0+3 of the read (garbage past rl is masked below)
+			uint32_t w4 = 0;
+			if (j0 < rl) {
+				if (staged) {
+					const uint32_t a = sbase + j0;
+					w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
+				} else {
+#pragma unroll
+					for (int u = 0; u < kStepUnroll; u++)
+						if (j0 + u < rl) w4 |= (uint32_t) gbase[j0 + u] << (8 * u);
+				}
 			}
-		}
-		for (uint32_t j0 = h - 1; j0 < wmax; j0 += kStepUnroll) {
-			unsigned long long kf[kStepUnroll], kr[kStepUnroll];
+			// codes: A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
+			// letter the code stands for (one byte permute)
+			const uint32_t t4 = (w4 >> 1) & 0x03030303u;
+			const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+			const uint32_t nib = code4 | (code4 >> 4);
+			const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+			const uint32_t left = rl > j0 ? rl - j0 : 0u;
+			const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
+			bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
+
 			uint2 ff[kStepUnroll], fr[kStepUnroll];              // FILTER: filter words
-			unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4]; // !FILTER: table buckets
-			uint32_t mf[kStepUnroll][2], mr[kStepUnroll][2];
+			uint32_t bsel_f[kStepUnroll], bsel_r[kStepUnroll];
+			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: keys and table buckets
+			unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4];
 #pragma unroll
 			for (int u = 0; u < kStepUnroll; u++) {
 				const uint32_t j = j0 + u;
-				if (j < rl) {
-					uint32_t c = decodeBase(s[j], bad);
-					hf = ((hf << 2) | c) & kmask;
-					hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
-					kf[u] = hf;
-					kr[u] = hr;
-					const unsigned long long xf = mixKey(hf), xr = mixKey(hr);
+				const uint32_t c = (code4 >> (8 * u)) & 3u;
+				hf = ((hf << 2) | c) & kmask;
+				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
+				if (j + 1 >= h && j < rl) {
 					if (FILTER) {
-						uint64_t wf, wr;
-						filterProbe(xf, p.filter_mask, wf, mf[u][0], mf[u][1]);
-						filterProbe(xr, p.filter_mask, wr, mr[u][0], mr[u][1]);
-						ff[u] = loadFilterWord(p.filter + wf, pol_keep);
-						fr[u] = loadFilterWord(p.filter + wr, pol_keep);
+						uint32_t af, ar;
+						filterHash(hf, af, bsel_f[u]);
+						filterHash(hr, ar, bsel_r[u]);
+						if (p.debug_flags & 4u) {
+							ff[u] = make_uint2(af, ar);
+							fr[u] = make_uint2(ar, af);
+						} else if (p.debug_flags & 1u) {
+							ff[u] = __ldg(p.filter + filterWordIndex(af, p.filter_shift));
+							fr[u] = __ldg(p.filter + filterWordIndex(ar, p.filter_shift));
+						} else {
+							ff[u] = loadFilterWord(p.filter + filterWordIndex(af, p.filter_shift), pol_keep);
+							fr[u] = loadFilterWord(p.filter + filterWordIndex(ar, p.filter_shift), pol_keep);
+						}
 					} else {
-						loadBucket(p.table + 2 * (xf & p.table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
-						loadBucket(p.table + 2 * (xr & p.table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
+						kf[u] = hf;
+						kr[u] = hr;
+						loadBucket(p.table + 2 * (mixKey(hf) & p.table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
+						loadBucket(p.table + 2 * (mixKey(hr) & p.table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
 					}
 				}
 			}
+			if (j0 + kStepUnroll >= h) { // warp-uniform: some step of this iteration has a full window
 #pragma unroll
-			for (int u = 0; u < kStepUnroll; u++) {
-				const uint32_t j = j0 + u;
-				bool cand_f = false, cand_r = false;
-				if (j < rl) {
-					n_probes += 2;
-					if (FILTER) {
-						cand_f = ((ff[u].x & mf[u][0]) == mf[u][0]) && ((ff[u].y & mf[u][1]) == mf[u][1]);
-						cand_r = ((fr[u].x & mr[u][0]) == mr[u][0]) && ((fr[u].y & mr[u][1]) == mr[u][1]);
-					} else {
-						// candidate = the bucket holds the key, or is full and the key may have spilled
-						cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
-						cand_r = br[u][0] == kr[u] || br[u][2] == kr[u] || (br[u][0] != kEmptyKey && br[u][2] != kEmptyKey);
+				for (int u = 0; u < kStepUnroll; u++) {
+					const uint32_t j = j0 + u;
+					bool cand_f = false, cand_r = false;
+					if (j + 1 >= h && j < rl) {
+						n_probes += 2;
+						if (FILTER) {
+							cand_f = filterTest(ff[u].x, ff[u].y, bsel_f[u]);
+							cand_r = filterTest(fr[u].x, fr[u].y, bsel_r[u]);
+						} else {
+							// candidate = the bucket holds the key, or is full and the key may have spilled
+							cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
+							cand_r = br[u][0] == kr[u] || br[u][2] == kr[u] || (br[u][0] != kEmptyKey && br[u][2] != kEmptyKey);
+						}
+					}
+					if (p.debug_flags & 2u) {
+						n_cand += cand_f + cand_r;
+						cand_f = cand_r = false;
+					}
+					if (cand_f) {
+						// forward strand, position i = j-h+1
+						uint32_t at = atomicAdd(&ws.q_count, 1u);
+						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
+						n_cand++;
+					}
+					if (cand_r) {
+						// reverse-complement strand: this window is rc position rl-1-j
+						uint32_t at = atomicAdd(&ws.q_count, 1u);
+						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
+						n_cand++;
 					}
 				}
-				if (cand_f) {
-					// forward strand, position i = j-h+1
-					uint32_t at = atomicAdd(&ws.q_count, 1u);
-					ws.queue[at] = ((uint32_t) lane << 16) | (j + 1 - h);
-					n_cand++;
-				}
-				if (cand_r) {
-					// reverse-complement strand: this window is rc position rl-1-j
-					uint32_t at = atomicAdd(&ws.q_count, 1u);
-					ws.queue[at] = ((uint32_t) lane << 16) | 0x8000u | (rl - 1 - j);
-					n_cand++;
-				}
+				__syncwarp();
+				// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
+				if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
+					drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 			}
-			__syncwarp();
-			// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
-			if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
-				drainQueue(p, ws, warp_spill, lane, n_leaf_hits, n_chained);
 		}
-		drainQueue(p, ws, warp_spill, lane, n_leaf_hits, n_chained);
+		const bool bad = bad4 != 0;
+		drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 
 		// ---- phase 3: thread per read: leaf set -> decision (query.cpp:529-636) ------------------
 		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;
 		const bool valid = have && !bad && rl >= h;
-		const uint32_t nh = valid ? min(ws.hit_cnt[lane], (uint32_t) (kHitSeg + kHitSpill)) : 0;
+		const uint32_t nh = valid ? min((uint32_t) ws.hit_cnt[lane], (uint32_t) (kHitSeg + kHitSpill)) : 0;
 		const uint32_t *my_spill = warp_spill + (size_t) lane * kHitSpill;
 		if (nh > 0) {
 			uint32_t min_r = 0xFFFFFFFFu, max_r = 0;
@@ -493,7 +564,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_reads_kernel(ScanParams 
 				p.read_nleaf_d[r] = distinct_d;
 			}
 		}
-		__syncwarp();
+		__syncwarp(); // every lane is done with this staging buffer and the warp state
+		cur = nxt;
 	}
 
 	// ---- block totals ---------------------------------------------------------------------------------
