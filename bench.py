@@ -408,6 +408,8 @@ def main():
                          "pack_ms_per_step": tm["pack_ms_sum"] / max(tm["steps"], 1),
                          "probes_per_step": stats["probes"], "bucket_hits_per_read": hits_per_read,
                          "chained_loads_per_step": stats["chained_loads"],
+                         "launch": {"grid": stats["grid_blocks"], "blocks_per_sm": stats["blocks_per_sm"],
+                                    "dyn_smem": stats["dyn_smem_bytes"], "regs": stats["regs_per_thread"]},
                          "probe_rate_gprobes_s": stats["probes"] / (scan_ms * 1e-3) / 1e9,
                          "random_sector_gather_gsectors_s": gsec,
                          "frac_of_random_gather": (stats["probes"] / (scan_ms * 1e-3) / 1e9) / gsec if gsec else None},

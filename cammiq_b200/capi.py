@@ -24,7 +24,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(_HERE, "libcammiq_gpu.so")
+    # CAMMIQ_LIB: experiments with alternative builds of the same ABI
+    return os.environ.get("CAMMIQ_LIB") or os.path.join(_HERE, "libcammiq_gpu.so")
 
 
 class CammiqError(RuntimeError):
@@ -78,7 +79,8 @@ class Timing(C.Structure):
                 ("scan_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("probes", C.c_uint64),
                 ("bucket_hits", C.c_uint64), ("leaf_hits", C.c_uint64), ("chained_loads", C.c_uint64),
                 ("pack_ms_sum", C.c_double), ("scan_ms_sum", C.c_double), ("reduce_ms_sum", C.c_double),
-                ("steps", C.c_uint64)]
+                ("steps", C.c_uint64), ("grid_blocks", C.c_uint32), ("blocks_per_sm", C.c_uint32),
+                ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32)]
 
 
 # every symbol include/cammiq_gpu.h declares: (restype, argtypes)

@@ -528,9 +528,17 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 			return fail(CQ_ECUDA, "scan kernel does not fit on an SM.");
 		c->last_dyn_smem[variant] = dyn_smem;
 		c->last_per_sm[variant] = std::min(per_sm, kMaxBlocksPerSM);
+		if (getenv("CAMMIQ_MAX_BLOCKS"))
+			c->last_per_sm[variant] = std::min(c->last_per_sm[variant], atoi(getenv("CAMMIQ_MAX_BLOCKS")));
+		cudaFuncAttributes fa;
+		if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess)
+			c->timing.regs_per_thread = (uint32_t) fa.numRegs;
 	}
 	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads; // one 32-read sub-tile per warp at least
 	c->grid = (int) std::min<uint64_t>((uint64_t) c->last_per_sm[variant] * c->n_sms, n_tiles);
+	c->timing.grid_blocks = (uint32_t) c->grid;
+	c->timing.blocks_per_sm = (uint32_t) c->last_per_sm[variant];
+	c->timing.dyn_smem_bytes = (uint32_t) dyn_smem;
 	void *args[] = {&sp};
 	CQ_CUDA(cudaLaunchKernel(kern, dim3(c->grid), dim3(kScanThreads), args, dyn_smem, c->stream));
 	c->timing.kernel_launches++;

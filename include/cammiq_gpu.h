@@ -232,6 +232,8 @@ typedef struct {
 	/* CUDA-event durations summed over every step since cq_timing_reset (or ctx creation) */
 	double pack_ms_sum, scan_ms_sum, reduce_ms_sum;
 	uint64_t steps;
+	/* geometry of the last scan launch */
+	uint32_t grid_blocks, blocks_per_sm, dyn_smem_bytes, regs_per_thread;
 } cq_timing;
 /* Synchronises the stream, folds the per-step CUDA events into the sums and returns them. */
 int cq_get_timing(cq_ctx *ctx, cq_timing *out);
