@@ -109,6 +109,7 @@ SYMBOLS = {
     "cq_sync": (C.c_int, [C.c_void_p]),
     "cq_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "cq_get_device_counters": (C.c_int, [C.c_void_p, C.POINTER(DeviceCounters)]),
+    "cq_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cq_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "cq_timing_reset": (C.c_int, [C.c_void_p]),
     "cq_bench_random_sectors": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),

@@ -77,6 +77,7 @@ struct cq_ctx {
 	uint64_t staged_reads = 0, staged_stride = 0, staged_bytes = 0;
 	bool staged_has_offsets = false;
 	uint32_t staged_max_len = 0;
+	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
 	size_t last_dyn_smem[4] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
 	int last_per_sm[4] = {0, 0, 0, 0};
 	// double-buffered host->device pipeline of cq_query
@@ -424,26 +425,31 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	if (n_reads > 0 && (bases == NULL || lengths == NULL))
 		return fail(CQ_EINVAL, "cq_reads_stage: NULL read buffers.");
 	CQ_CUDA(cudaSetDevice(c->device));
-	// extent of the base buffer and the longest read (sets the shared-memory tile size)
-	uint64_t total = 0;
+	// byte range the reads span in the caller's buffer, and the longest read (sets the tile size)
+	uint64_t lo = ~0ull, hi = 0;
 	uint32_t max_len = 1;
 	for (uint64_t i = 0; i < n_reads; i++) {
-		uint64_t end = (offsets ? offsets[i] : i * stride) + lengths[i];
-		total = std::max(total, end);
+		uint64_t off = offsets ? offsets[i] : i * stride;
+		lo = std::min(lo, off);
+		hi = std::max(hi, off + lengths[i]);
 		max_len = std::max<uint32_t>(max_len, lengths[i]);
 	}
+	if (hi < lo) lo = hi = 0;
+	const uint64_t copy_lo = lo & ~15ull, total = hi - copy_lo;
 	int rc;
-	if ((rc = ensure(&c->d_bases, &c->cap_bases, total + 16)) != 0) return rc;
+	if ((rc = ensure(&c->d_bases, &c->cap_bases, total + 32)) != 0) return rc;
 	if ((rc = ensure(&c->d_lengths, &c->cap_reads_len, n_reads)) != 0) return rc;
 	if (offsets && (rc = ensure(&c->d_offsets, &c->cap_reads_off, n_reads)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(c->ev[0], c->stream));
 	if (n_reads > 0) {
-		CQ_CUDA(cudaMemcpyAsync(c->d_bases, bases, total, cudaMemcpyHostToDevice, c->stream));
+		if (total > 0)
+			CQ_CUDA(cudaMemcpyAsync(c->d_bases, bases + copy_lo, total, cudaMemcpyHostToDevice, c->stream));
 		CQ_CUDA(cudaMemcpyAsync(c->d_lengths, lengths, n_reads, cudaMemcpyHostToDevice, c->stream));
 		if (offsets)
 			CQ_CUDA(cudaMemcpyAsync(c->d_offsets, offsets, n_reads * 8, cudaMemcpyHostToDevice, c->stream));
 	}
 	CQ_CUDA(cudaEventRecord(c->ev[1], c->stream));
+	c->staged_shift = copy_lo;
 	c->staged_reads = n_reads;
 	c->staged_stride = stride;
 	c->staged_has_offsets = offsets != NULL;
@@ -619,7 +625,7 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 	if ((rc = beginStep(c, &sev)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
-	ReadBatch rb = {c->d_bases, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
+	ReadBatch rb = {c->d_bases - c->staged_shift, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
 		c->staged_reads, 0, c->staged_max_len};
 	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
@@ -810,6 +816,13 @@ extern "C" int cq_get_device_counters(cq_ctx *c, cq_device_counters *out) {
 	out->n_rcount_u = c->n_leaves_u;
 	out->d_rcount_d = c->d_rcount_d;
 	out->n_rcount_d = c->n_leaves_d;
+	return CQ_OK;
+}
+
+extern "C" int cq_get_stream(cq_ctx *c, void **stream) {
+	if (c == NULL || stream == NULL)
+		return fail(CQ_EINVAL, "cq_get_stream: NULL argument.");
+	*stream = (void *) c->stream;
 	return CQ_OK;
 }
 

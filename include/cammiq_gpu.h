@@ -222,6 +222,8 @@ typedef struct {
 	uint64_t n_rcount_d;
 } cq_device_counters;
 int cq_get_device_counters(cq_ctx *ctx, cq_device_counters *out);
+/* The cudaStream_t every call of this context enqueues on (for the caller's collectives). */
+int cq_get_stream(cq_ctx *ctx, void **stream);
 
 typedef struct {
 	double h2d_ms, pack_ms, scan_ms, reduce_ms, d2h_ms, total_ms; /* last cq_query / cq_query_staged */

@@ -75,5 +75,31 @@ def main():
             sum(f["cd"]), size))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def make_cli_expectations():
+    """Outputs of the UNMODIFIED reference CLI (oracle/_ref/cammiq_ref) on every case: the
+    --read_cnts output file and the counter lines of its stderr, for the drop-in CLI test."""
+    import re
+    import subprocess
+    for name in CASES:
+        d = os.path.join(HERE, name)
+        base = [synth.CAMMIQ_REF, "--query", "-f", os.path.join(d, "genome_map.out"), "-q",
+                os.path.join(d, "reads.fq"), "-i", os.path.join(d, "index_u.bin1"), os.path.join(d, "index_d.bin2")]
+        out = os.path.join(d, "ref_cli_read_cnts.out")
+        r1 = subprocess.run(base[:2] + ["--read_cnts"] + base[2:] + ["-o", out], capture_output=True, text=True)
+        r2 = subprocess.run(base + ["-o", os.path.join("/tmp", "unused.out")], capture_output=True, text=True)
+        assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+        keep = re.compile(r"^(Querying|Number of|Completed query|Hash Length)")
+        with open(os.path.join(d, "ref_cli_stderr.txt"), "w") as f:
+            for tag, r in (("read_cnts", r1), ("standard", r2)):
+                for line in r.stderr.replace("\r", "\n").split("\n"):
+                    if keep.match(line):
+                        f.write(tag + "\t" + line + "\n")
+        print(name, open(out).read().strip().split("\n")[-1][:80])
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cli":
+    make_cli_expectations()
