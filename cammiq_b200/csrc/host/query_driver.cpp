@@ -385,9 +385,11 @@ void FqReader::dumpIlpInputs(size_t file_idx) {
 		for (uint32_t g = 1; g <= G; g++)
 			for (uint64_t k = off[g]; k < off[g + 1]; k++) {
 				uint64_t l = ids[k];
-				double d = lv.depth[l];
-				double w1 = rl ? (lv.ucount1[l] * (rl - d) * 1.0 / rl) * pow(1 - erate_, d) : 0.0;
-				double w2 = rl ? (lv.ucount2[l] * (rl - d) * 1.0 / rl) * pow(1 - erate_, d) : 0.0;
+				// runILP_* receives erate as a double converted from the float option (query.cpp:252)
+				const double er = erate_;
+				const uint32_t d = lv.depth[l];
+				double w1 = rl ? (lv.ucount1[l] * (rl - d) * 1.0 / rl) * pow(1 - er, d) : 0.0;
+				double w2 = rl ? (lv.ucount2[l] * (rl - d) * 1.0 / rl) * pow(1 - er, d) : 0.0;
 				fprintf(f, "%s\t%u\t%lu\t%u\t%u\t%u\t%u\t%u\t%u\t%.17g\t%.17g\n", table == 0 ? "LEAFU" : "LEAFD", g,
 					(unsigned long) l, lv.ref_id1[l], lv.ref_id2[l], lv.ucount1[l], lv.ucount2[l], lv.depth[l], rc[l], w1, w2);
 			}

@@ -83,6 +83,6 @@ def test_cli_ilp_inputs_dump(tmp_path):
         assert len(leaf_rows) == len(ids)
         for r, l in zip(leaf_rows, ids):
             l = int(l)
-            assert int(r[2]) == l and int(r[9]) == int(rc[l])
-            w1 = oi.ucount1[l] * (rl - float(oi.depth[l])) / rl * (1 - np.float32(0.01)) ** float(oi.depth[l])
-            assert abs(float(r[10]) - w1) <= 1e-9 * max(1.0, abs(w1))
+            assert int(r[2]) == l and int(r[8]) == int(rc[l])
+            w1 = float(oi.ucount1[l]) * (rl - float(oi.depth[l])) / rl * (1.0 - float(np.float32(0.01))) ** float(oi.depth[l])
+            assert abs(float(r[9]) - w1) <= 1e-9 * max(1.0, abs(w1))
