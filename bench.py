@@ -224,6 +224,7 @@ def main():
     import torch.distributed as dist
 
     import cammiq_b200 as cq
+    from cammiq_b200 import multigpu
     from cammiq_b200 import synthlib as sl
 
     rank = int(os.environ.get("RANK", "0"))
@@ -266,11 +267,10 @@ def main():
     def combine():
         # the one collective of the path: sum the counter block (and the per-leaf rcount in
         # mode P) into rank 0 over NCCL
-        if world > 1:
-            dist.reduce(counts, dst=0)
-            if mode == cq.MODE_P:
-                dist.reduce(rc_u, dst=0)
-                dist.reduce(rc_d, dst=0)
+        if mode == cq.MODE_P:
+            multigpu.combine_counters(counts, rc_u, rc_d)
+        else:
+            multigpu.combine_counters(counts)
 
     def barrier():
         if world > 1:
@@ -316,6 +316,21 @@ def main():
     ctx.query_staged(mode)
     ctx.sync()
     mine = ctx.fetch(mode)
+    multi_check = None
+    if world > 1:
+        # the combined counters on rank 0 must equal the sum of the per-rank results
+        local = torch.tensor([int(mine["nundet"]), int(mine["nconf"]), int(mine["cnt_u"].sum()),
+                              int(mine["cnt_d"].sum()), int(mine["rcount_u"].sum()) if mode == cq.MODE_P else 0],
+                             device="cuda", dtype=torch.int64)
+        dist.all_reduce(local)
+        combine()
+        torch.cuda.synchronize()
+        if rank == 0:
+            tot = ctx.fetch(mode)
+            got = [int(tot["nundet"]), int(tot["nconf"]), int(tot["cnt_u"].sum()), int(tot["cnt_d"].sum()),
+                   int(tot["rcount_u"].sum()) if mode == cq.MODE_P else 0]
+            multi_check = "ok" if got == local.tolist() else "MISMATCH %s vs %s" % (got, local.tolist())
+        dist.barrier()
     stats = ctx.timing()
     rcount_updates = (int(mine["rcount_u"].sum()) + int(mine["rcount_d"].sum())) if mode == cq.MODE_P else 0
     valid_reads = n - int(mine["n_invalid"])
@@ -415,6 +430,7 @@ def main():
                          "frac_of_random_gather": (stats["probes"] / (scan_ms * 1e-3) / 1e9) / gsec if gsec else None},
             "cpu_baseline": cpu,
             "parity_vs_reference_sample": parity,
+            "multi_gpu_reduce_check": multi_check,
             "result": {"nundet": int(mine["nundet"]), "nconf": int(mine["nconf"]),
                        "sum_u": int(mine["cnt_u"].sum()), "sum_d": int(mine["cnt_d"].sum())},
         }
