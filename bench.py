@@ -146,7 +146,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def impl_reference(args, w, name):
+def impl_reference(args, w, name, json_fd):
     """Reference arm: the reference's own OpenMP scan (query64mt_p) on this box's host cores,
     on a bounded sample of the same workload per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -176,7 +176,7 @@ def impl_reference(args, w, name):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json_fd, line)
     return 0
 
 
@@ -199,6 +199,24 @@ def oracle_port_rows(d, w, reps):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version
+    # banner, ...) is diverted to stderr at the file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return run(json_fd)
+    finally:
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        os.close(json_fd)
+
+
+def emit(json_fd, line):
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def run(json_fd):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -218,7 +236,7 @@ def main():
         w["reads"] = args.reads
         w["sample_reads"] = min(w["sample_reads"], args.reads)
     if args.impl == "reference":
-        return impl_reference(args, w, name)
+        return impl_reference(args, w, name, json_fd)
 
     import torch
     import torch.distributed as dist
@@ -434,7 +452,7 @@ def main():
             "result": {"nundet": int(mine["nundet"]), "nconf": int(mine["nconf"]),
                        "sum_u": int(mine["cnt_u"].sum()), "sum_d": int(mine["cnt_d"].sum())},
         }
-        print(json.dumps(line), flush=True)
+        emit(json_fd, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

