@@ -106,7 +106,7 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 		if (fi.table[i].key == kEmptyKey)
 			continue;
 		uint32_t A, B;
-		filterHash(fi.table[i].key, A, B);
+		filterHash(canonicalKeyHost(fi.table[i].key, fi.hash_len), A, B);
 		fi.filter[filterWordIndex(A, fi.filter_shift)] |= filterMask(B);
 	}
 }
@@ -116,7 +116,7 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 	if (!fi.filter.empty()) {
 		// same gate as phase 1 of the scan kernel: a filter miss ends the lookup
 		uint32_t A, B;
-		filterHash(bucket, A, B);
+		filterHash(canonicalKeyHost(bucket, fi.hash_len), A, B);
 		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_shift)];
 		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
 			return UINT64_MAX;

@@ -50,8 +50,25 @@ inline uint64_t mixKey(uint64_t x) {
 // them without touching DRAM.  The filter hash is deliberately lean (6 integer multiplies,
 // 32-bit only): it runs twice per read position.  Word index = top bits of A, bit
 // selectors = top 20 bits of B; (f, g) keep the 62-bit key injective before mixing.
+// The filter is keyed by the CANONICAL h-mer, min(key, reverse complement of key): the scan
+// holds both strands' hashes of a window anyway (hf, hr), so one filter probe per read
+// position answers both strands -- half the L2 requests of probing each strand's hash.
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
 static const uint32_t kFilterMinBitsPerKey = 3;
+
+// reverse complement of a 2-bit packed h-mer (first base most significant)
+inline uint64_t revcompKeyHost(uint64_t key, uint32_t h) {
+	uint64_t x = ~key, r = 0;
+	for (uint32_t i = 0; i < h; i++) {
+		r = (r << 2) | (x & 3u);
+		x >>= 2;
+	}
+	return r;
+}
+inline uint64_t canonicalKeyHost(uint64_t key, uint32_t h) {
+	uint64_t rc = revcompKeyHost(key, h);
+	return key < rc ? key : rc;
+}
 
 #if defined(__CUDACC__)
 __host__ __device__

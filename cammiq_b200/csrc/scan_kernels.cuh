@@ -376,8 +376,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 			const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
 			bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
 
-			uint2 ff[kStepUnroll], fr[kStepUnroll];              // FILTER: filter words
-			uint32_t bsel_f[kStepUnroll], bsel_r[kStepUnroll];
+			uint2 ff[kStepUnroll];                                // FILTER: filter words
+			uint32_t bsel[kStepUnroll];
 			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: keys and table buckets
 			unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4];
 #pragma unroll
@@ -388,19 +388,14 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
 				if (j + 1 >= h && j < rl) {
 					if (FILTER) {
-						uint32_t af, ar;
-						filterHash(hf, af, bsel_f[u]);
-						filterHash(hr, ar, bsel_r[u]);
-						if (p.debug_flags & 4u) {
-							ff[u] = make_uint2(af, ar);
-							fr[u] = make_uint2(ar, af);
-						} else if (p.debug_flags & 1u) {
-							ff[u] = __ldg(p.filter + filterWordIndex(af, p.filter_shift));
-							fr[u] = __ldg(p.filter + filterWordIndex(ar, p.filter_shift));
-						} else {
-							ff[u] = loadFilterWord(p.filter + filterWordIndex(af, p.filter_shift), pol_keep);
-							fr[u] = loadFilterWord(p.filter + filterWordIndex(ar, p.filter_shift), pol_keep);
-						}
+						// hr is the reverse complement of the window hf covers: ONE probe with the
+						// canonical h-mer answers both strands
+						uint32_t a;
+						filterHash(hf < hr ? hf : hr, a, bsel[u]);
+						if (p.debug_flags & 4u)
+							ff[u] = make_uint2(a, bsel[u]);
+						else
+							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_shift), pol_keep);
 					} else {
 						kf[u] = hf;
 						kr[u] = hr;
@@ -417,8 +412,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 					if (j + 1 >= h && j < rl) {
 						n_probes += 2;
 						if (FILTER) {
-							cand_f = filterTest(ff[u].x, ff[u].y, bsel_f[u]);
-							cand_r = filterTest(fr[u].x, fr[u].y, bsel_r[u]);
+							cand_f = cand_r = filterTest(ff[u].x, ff[u].y, bsel[u]);
 						} else {
 							// candidate = the bucket holds the key, or is full and the key may have spilled
 							cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
