@@ -106,8 +106,9 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 		if (fi.table[i].key == kEmptyKey)
 			continue;
 		uint32_t A, B;
-		filterHash(canonicalKeyHost(fi.table[i].key, fi.hash_len), A, B);
-		fi.filter[filterWordIndex(A, fi.filter_shift)] |= filterMask(B);
+		const uint64_t key = fi.table[i].key, canon = canonicalKeyHost(key, fi.hash_len);
+		filterHash(canon, A, B);
+		fi.filter[filterWordIndex(A, fi.filter_shift)] |= filterMask(key == canon ? B : filterOtherPattern(B));
 	}
 }
 
@@ -116,9 +117,10 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 	if (!fi.filter.empty()) {
 		// same gate as phase 1 of the scan kernel: a filter miss ends the lookup
 		uint32_t A, B;
-		filterHash(canonicalKeyHost(bucket, fi.hash_len), A, B);
+		const uint64_t canon = canonicalKeyHost(bucket, fi.hash_len);
+		filterHash(canon, A, B);
 		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_shift)];
-		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
+		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), bucket == canon ? B : filterOtherPattern(B)))
 			return UINT64_MAX;
 	}
 	uint64_t b = mixKey(bucket) & mask;

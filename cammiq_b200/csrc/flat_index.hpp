@@ -82,6 +82,14 @@ inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
 	A *= 0x27D4EB2Fu;
 	B = (g ^ A) * 0x165667B1u;
 }
+// The filter remembers WHICH orientation of the canonical h-mer is a key: a key equal to its
+// canonical form sets the bit pattern of B, a key that is the reverse complement of its
+// canonical form sets the pattern of filterOtherPattern(B).  A probe tests both patterns of
+// the one word it loaded and queues only the strand(s) that can hold the key.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t filterOtherPattern(uint32_t B) { return (B >> 12) * 0x2C1B3C6Du + 0x9E3779B9u; } // only the selector bits of B
 // word index for a filter of 2^(32 - shift) words
 #if defined(__CUDACC__)
 __host__ __device__

@@ -392,6 +392,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 						// canonical h-mer answers both strands
 						uint32_t a;
 						filterHash(hf < hr ? hf : hr, a, bsel[u]);
+						// the two lowest bits of B are unused by the selectors: remember the orientation
+						bsel[u] = (bsel[u] & ~3u) | (hf <= hr ? 1u : 0u) | (hf == hr ? 2u : 0u);
 						if (p.debug_flags & 4u)
 							ff[u] = make_uint2(a, bsel[u]);
 						else
@@ -412,7 +414,13 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 					if (j + 1 >= h && j < rl) {
 						n_probes += 2;
 						if (FILTER) {
-							cand_f = cand_r = filterTest(ff[u].x, ff[u].y, bsel[u]);
+							// pattern of B: the canonical orientation is a key; other pattern: its reverse
+							// complement is.  fwd_canon says which strand holds the canonical orientation.
+							const bool same = filterTest(ff[u].x, ff[u].y, bsel[u]);
+							const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
+							const bool fwd_canon = (bsel[u] & 1u) != 0, palin = (bsel[u] & 2u) != 0;
+							cand_f = fwd_canon ? same : other;
+							cand_r = (fwd_canon && !palin) ? other : same;
 						} else {
 							// candidate = the bucket holds the key, or is full and the key may have spilled
 							cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
