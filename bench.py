@@ -47,11 +47,13 @@ def log(*a):
 def synth_params(w, threads=0):
     from cammiq_b200 import synthlib as sl
     return sl.params(seed=w["seed"], n_genomes=w["n_genomes"], genome_len=w["genome_len"],
-                     cluster_size=w["cluster_size"], k=w["k"], lmax=w["lmax"], threads=threads)
+                     cluster_size=w["cluster_size"], k=w["k"], lmax=w["lmax"], threads=threads,
+                     permille_deep=w.get("permille_deep", 50))
 
 
 def workdir_for(name, w, base):
-    return os.path.join(base, "cammiq_bench_%s_g%d_l%d_s%d" % (name, w["n_genomes"], w["genome_len"], w["seed"]))
+    return os.path.join(base, "cammiq_bench_%s_g%d_l%d_s%d_d%d" % (name, w["n_genomes"], w["genome_len"], w["seed"],
+                                                                    w.get("permille_deep", 50)))
 
 
 def ensure_index(name, w, base):
@@ -227,11 +229,14 @@ def run(json_fd):
     ap.add_argument("--workdir", default=os.environ.get("CAMMIQ_BENCH_DIR", "/tmp"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="p", choices=["p", "sc"])
+    ap.add_argument("--deep-permille", type=int, default=-1, help="override the share of keys longer than h (synthetic index)")
     ap.add_argument("--filter-mb", type=float, default=-1, help="override the membership-filter budget (MB, 0 = none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cammiq" else max(args.warmup, 1)
     name = args.workload
     w = dict(WORKLOADS[name])
+    if args.deep_permille >= 0:
+        w["permille_deep"] = args.deep_permille
     if args.reads:
         w["reads"] = args.reads
         w["sample_reads"] = min(w["sample_reads"], args.reads)

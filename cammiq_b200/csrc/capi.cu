@@ -158,8 +158,8 @@ extern "C" int cq_index_get_info(const cq_index *idx, cq_index_info *info) {
 	info->n_buckets_d = f.d.bucket_key.size();
 	info->n_keys = f.n_keys;
 	info->n_table_buckets = f.n_table_buckets;
-	info->n_nodes_u = f.cnodes_u.size() / 4;
-	info->n_nodes_d = f.cnodes_d.size() / 4;
+	info->n_nodes_u = f.u.numNodes();
+	info->n_nodes_d = f.d.numNodes();
 	info->max_ref_id = std::max(f.u.max_ref_id, f.d.max_ref_id);
 	info->filter_bytes = f.filter.size() * 8;
 	info->device_bytes = f.deviceBytes();
@@ -333,8 +333,8 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	freeDevice(c);
 	int rc;
 	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), c->stream)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_nodes_u, f.cnodes_u.data(), f.cnodes_u.size(), c->stream)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_nodes_d, f.cnodes_d.data(), f.cnodes_d.size(), c->stream)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), c->stream)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), c->stream)) != 0) return rc;
 	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), c->stream)) != 0) return rc;
 	std::vector<uint2> dref(f.d.numLeaves());
 	for (size_t i = 0; i < dref.size(); i++)

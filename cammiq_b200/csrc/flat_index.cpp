@@ -7,61 +7,11 @@
 namespace cammiq {
 
 uint64_t FlatIndex::deviceBytes() const {
-	return table.size() * sizeof(TableSlot) + filter.size() * 8 + (cnodes_u.size() + cnodes_d.size()) * 4 +
+	return table.size() * sizeof(TableSlot) + filter.size() * 8 + (u.nodes.size() + d.nodes.size()) * 4 +
 		u.numLeaves() * 4 + d.numLeaves() * 8 + (u.numLeaves() + d.numLeaves()) * 4;
 }
 
 namespace {
-
-// Path compression of one decoded trie (x.nodes) into out; returns the new ref of `ref`.
-uint32_t compressTrie(const DecodedIndex &x, uint32_t ref, std::vector<uint32_t> &out) {
-	if (ref == kRefNone || refIsLeaf(ref))
-		return ref;
-	const uint32_t *c = &x.nodes[4 * (size_t) refNodeId(ref)];
-	int n_children = 0, only = -1;
-	for (int i = 0; i < 4; i++)
-		if (c[i] != kRefNone) {
-			n_children++;
-			only = i;
-		}
-	if (n_children == 1) {
-		// maximal single-child path starting here, at most kChainMaxBases long
-		uint64_t bases = 0;
-		uint32_t len = 0, cur = ref;
-		for (;;) {
-			const uint32_t *cc = &x.nodes[4 * (size_t) refNodeId(cur)];
-			int cnt = 0, code = -1;
-			for (int i = 0; i < 4; i++)
-				if (cc[i] != kRefNone) {
-					cnt++;
-					code = i;
-				}
-			if (cnt != 1 || len == kChainMaxBases)
-				break;
-			bases |= (uint64_t) code << (62 - 2 * len);
-			len++;
-			cur = cc[code];
-			if (cur == kRefNone || refIsLeaf(cur))
-				break;
-		}
-		size_t at = out.size();
-		out.insert(out.end(), 4, 0u);
-		uint32_t child = compressTrie(x, cur, out);
-		out[at + 0] = child;
-		out[at + 1] = len;
-		out[at + 2] = (uint32_t) (bases >> 32);
-		out[at + 3] = (uint32_t) bases;
-		(void) only;
-		return kRefChainTag | (uint32_t) (at / 4);
-	}
-	size_t at = out.size();
-	out.insert(out.end(), 4, 0u);
-	for (int i = 0; i < 4; i++) {
-		uint32_t child = compressTrie(x, c[i], out);
-		out[at + i] = child;
-	}
-	return (uint32_t) (at / 4) + 1;
-}
 
 // Insert (or find) key; returns the slot.  Linear probing by bucket.
 inline TableSlot *probeInsert(std::vector<TableSlot> &t, uint64_t mask, uint64_t key, bool &fresh) {
@@ -121,16 +71,10 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 			n_keys += fresh ? 1 : 0;
 			// a repeated key inside one file: the later bucket replaces the earlier one, as
 			// map64[bucket] = root does (hashtrie.cpp:500)
-			std::vector<uint32_t> &cn = t == 0 ? out.cnodes_u : out.cnodes_d;
-			uint32_t root = compressTrie(x, x.bucket_root[i], cn);
-			if (cn.size() / 4 >= kRefChainTag) {
-				err = "Index has more than 2^30 trie nodes.";
-				return CQ_EFORMAT;
-			}
 			if (t == 0)
-				s->u_ref = root;
+				s->u_ref = x.bucket_root[i];
 			else
-				s->d_ref = root;
+				s->d_ref = x.bucket_root[i];
 		}
 	}
 	out.n_keys = n_keys;
@@ -196,32 +140,17 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 			break;
 		b = (b + 1) & mask;
 	}
-	const std::vector<uint32_t> &cn = table == CQ_TABLE_U ? fi.cnodes_u : fi.cnodes_d;
+	const DecodedIndex &x = table == CQ_TABLE_U ? fi.u : fi.d;
 	size_t i = 0;
 	while (ref != kRefNone) {
 		if (refIsLeaf(ref))
 			return refLeafId(ref);
-		if (ref & kRefChainTag) {
-			const uint32_t *n = &cn[4 * (size_t) (ref & ~kRefChainTag)];
-			const uint32_t L = n[1];
-			const uint64_t bases = ((uint64_t) n[2] << 32) | n[3];
-			if (len - i < L)
-				return UINT64_MAX; // the read ends inside the chain (or mismatches before)
-			for (uint32_t k = 0; k < L; k++) {
-				int code = baseCode(cand[i + k]);
-				if (code < 0 || (uint32_t) code != ((bases >> (62 - 2 * k)) & 3u))
-					return UINT64_MAX;
-			}
-			i += L;
-			ref = n[0];
-			continue;
-		}
 		if (i >= len)
 			return UINT64_MAX;
 		int code = baseCode(cand[i++]);
 		if (code < 0)
 			return UINT64_MAX;
-		ref = cn[4 * (size_t) refNodeId(ref) + code];
+		ref = x.nodes[4 * (size_t) refNodeId(ref) + code];
 	}
 	return UINT64_MAX;
 }

@@ -5,11 +5,8 @@
 //                  length (query.cpp:460), so ONE probe answers both tables.  Linear probing
 //                  by bucket; a lookup stops at the first bucket that holds the key or has a
 //                  free slot, so at the default load factor a miss costs one sector.
-//   trie nodes     per table, 16 bytes per node, PATH-COMPRESSED: a branch node holds 4 child
-//                  refs; a chain node holds up to 32 bases of a single-child path plus the ref
-//                  below it.  Almost every trie of a real index is one chain to one leaf
-//                  (SURVEY.md Appendix A.5), so a key longer than h costs one extra sector
-//                  instead of one dependent HBM access per base.
+//   trie nodes     per table, 4 child refs (16 bytes) per internal node; only buckets whose
+//                  root is not already a leaf have any (rare when h == k).
 //   leaf refs      per table, the genome id(s) the classification needs: u32 for U,
 //                  {u32,u32} for D.  The remaining leaf fields (ucount, depth) stay on the
 //                  host for the ILP set-up.
@@ -111,15 +108,6 @@ inline uint64_t filterMask(uint32_t B) {
 	return (uint64_t) lo | ((uint64_t) hi << 32);
 }
 
-// Compressed-trie refs (table slots and node children):
-//   0                     none
-//   0x80000000 | leaf     leaf (file-order id)                       [as in the decoded index]
-//   0x40000000 | node     chain node  {child ref, length L (1..32), bases hi32, bases lo32}
-//                          bases: 2 bits each, first base most significant, left-aligned in 64 bits
-//   node + 1              branch node {ref A, ref C, ref G, ref T}
-static const uint32_t kRefChainTag = 0x40000000u;
-static const uint32_t kChainMaxBases = 32;
-
 struct FlatIndex {
 	uint32_t hash_len = 0;
 	uint64_t n_table_buckets = 0; // power of two
@@ -127,8 +115,7 @@ struct FlatIndex {
 	std::vector<TableSlot> table; // n_table_buckets * kSlotsPerBucket
 	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
 	uint32_t filter_shift = 0;    // 32 - log2(filter words)
-	DecodedIndex u, d;            // leaves (file order) + decoded tries + buckets of each table
-	std::vector<uint32_t> cnodes_u, cnodes_d; // path-compressed tries, 4 words per node
+	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
 	double decode_ms = 0, flatten_ms = 0;
 
 	uint64_t deviceBytes() const;

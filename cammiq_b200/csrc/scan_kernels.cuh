@@ -158,9 +158,6 @@ struct WarpState {
 	uint8_t rl[32];
 	uint32_t q_count;
 	uint32_t staged;               // sub-tile is in shared memory (else: read from global)
-	uint32_t stats[4];             // candidates, leaf hits, chained bucket loads, (unused)
-	uint32_t tally[3];             // unlabeled, conflict, invalid reads seen by this warp
-	uint32_t pad_;
 	uint64_t bar;                  // mbarrier of the warp's staging buffer
 };
 
@@ -176,7 +173,20 @@ __device__ __forceinline__ uint32_t strandBase(const uint8_t *s, uint32_t rl, ui
 	return c;
 }
 
-__device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
+// Walk the CSR trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).
+__device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes,
+		const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t next) {
+	while (ref != kRefNone && !(ref & kRefLeafTag)) {
+		if (next >= rl)
+			return kRefNone;
+		uint32_t code = strandBase(s, rl, strand, next);
+		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
+		next++;
+	}
+	return ref;
+}
+
+__device__ __forceinline__ uint32_t ldsWord(uint32_t addr) {
 	uint32_t v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
@@ -188,15 +198,19 @@ __device__ __forceinline__ unsigned long long reverseGroups(unsigned long long x
 	return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
 }
 
-// 2-bit packing of the FORWARD bases [i, i+n) of a read, n <= 32, first base most significant,
-// right-aligned (bytes were validated by phase 1)
-__device__ __forceinline__ unsigned long long forwardWindow(const uint8_t *s, bool in_smem, uint32_t i, uint32_t n) {
+// 2-bit packing of bases [j, j+n) of strand `strand` of a read (n <= 32, first base most
+// significant, right-aligned).  The reverse-complement strand's window is the reverse
+// complement of the forward window [rl-j-n, rl-j); staged reads are decoded four bases per
+// 32-bit shared load (the bytes were validated by phase 1).
+__device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, bool in_smem, uint32_t rl, uint32_t strand,
+		uint32_t j, uint32_t n) {
+	const uint32_t i = strand ? rl - j - n : j;
 	unsigned long long hv = 0;
 	if (in_smem) {
 		const uint32_t a0 = smemAddr(s) + i;
 		for (uint32_t t = 0; t < n; t += 4) {
 			const uint32_t a = a0 + t;
-			const uint32_t w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
+			const uint32_t w4 = __funnelshift_r(ldsWord(a & ~3u), ldsWord((a & ~3u) + 4u), (a & 3u) * 8u);
 			const uint32_t t4 = (w4 >> 1) & 0x03030303u;
 			const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
 #pragma unroll
@@ -208,58 +222,16 @@ __device__ __forceinline__ unsigned long long forwardWindow(const uint8_t *s, bo
 		for (uint32_t t = 0; t < n; t++)
 			hv = (hv << 2) | decodeBase(s[i + t], bad);
 	}
-	return hv;
-}
-
-// the same for strand `strand` (1 = reverse complement): bases [j, j+n) of that strand
-__device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, bool in_smem, uint32_t rl, uint32_t strand,
-		uint32_t j, uint32_t n) {
-	if (!strand)
-		return forwardWindow(s, in_smem, j, n);
-	// rc[j .. j+n) is the reverse complement of fwd[rl-j-n .. rl-j)
-	return reverseGroups(~forwardWindow(s, in_smem, rl - j - n, n)) >> (64 - 2 * n);
-}
-
-// Walk the path-compressed trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).
-// A chain node swallows up to 32 bases with one 16-byte load; a branch node one base.
-__device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes,
-		const uint8_t *s, bool in_smem, uint32_t rl, uint32_t strand, uint32_t next) {
-	while (ref != kRefNone && !(ref & kRefLeafTag)) {
-		if (ref & kRefChainTag) {
-			uint4 n;
-			asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-				: "=r"(n.x), "=r"(n.y), "=r"(n.z), "=r"(n.w) : "l"(nodes + 4 * (size_t) (ref & ~kRefChainTag)));
-			const uint32_t L = n.y;
-			if (rl - next < L)
-				return kRefNone; // the read ends inside the chain
-			const unsigned long long seg = (((unsigned long long) n.z << 32) | n.w) >> (64 - 2 * L);
-			if (strandWindow(s, in_smem, rl, strand, next, L) != seg)
-				return kRefNone;
-			next += L;
-			ref = n.x;
-		} else {
-			if (next >= rl)
-				return kRefNone;
-			uint32_t code = strandBase(s, rl, strand, next);
-			ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
-			next++;
-		}
-	}
-	return ref;
+	return strand ? reverseGroups(~hv) >> (64 - 2 * n) : hv;
 }
 
 // Phase 2: the warp drains its candidate queue.  One candidate per lane: recompute the h-mer,
-// probe the prefix table (HBM), descend the path-compressed trie, append leaf ids to the owning
-// read's hit list.  A separate function on purpose: the probe loop of phase 1 keeps its own
-// register allocation whatever this code needs.
-__device__ __noinline__ void drainQueue(const ScanParams *pp, WarpState *wsp, const uint8_t *buf, uint32_t *warp_spill) {
-	const ScanParams &p = *pp;
-	WarpState &ws = *wsp;
-	const int lane = threadIdx.x & 31;
+// probe the prefix table (HBM), descend, append leaves to the owning read's hit list.
+__device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, const uint8_t *buf, uint32_t *warp_spill,
+		int lane, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
 	const uint32_t nq = ws.q_count;
 	const uint32_t h = p.h;
-	uint32_t n_leaf_hits = 0, n_chained = 0;
 	for (uint32_t base = 0; base < nq; base += 32) {
 		const uint32_t k = base + lane;
 		if (k < nq) {
@@ -267,8 +239,7 @@ __device__ __noinline__ void drainQueue(const ScanParams *pp, WarpState *wsp, co
 			const uint32_t slot = item >> 9, strand = (item >> 8) & 1u, pos = item & 0xFFu;
 			const uint8_t *s = slotBases(p, ws, buf, slot);
 			const uint32_t rl = ws.rl[slot];
-			const bool in_smem = ws.staged != 0;
-			const unsigned long long hv = strandWindow(s, in_smem, rl, strand, pos, h);
+			const unsigned long long hv = strandWindow(s, ws.staged != 0, rl, strand, pos, h);
 			uint64_t b = mixKey(hv) & p.table_mask;
 			unsigned long long k0, r0, k1, r1, refs = 0;
 			bool found = false;
@@ -283,8 +254,8 @@ __device__ __noinline__ void drainQueue(const ScanParams *pp, WarpState *wsp, co
 			}
 			if (found) {
 				uint32_t leaf[2];
-				leaf[0] = descend((uint32_t) refs, p.nodes_u, s, in_smem, rl, strand, pos + h);
-				leaf[1] = descend((uint32_t) (refs >> 32), p.nodes_d, s, in_smem, rl, strand, pos + h);
+				leaf[0] = descend((uint32_t) refs, p.nodes_u, s, rl, strand, pos + h);
+				leaf[1] = descend((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, pos + h);
 #pragma unroll
 				for (int t = 0; t < 2; t++) {
 					if (leaf[t] == kRefNone)
@@ -301,262 +272,20 @@ __device__ __noinline__ void drainQueue(const ScanParams *pp, WarpState *wsp, co
 			}
 		}
 	}
-	n_leaf_hits = __reduce_add_sync(0xffffffffu, n_leaf_hits);
-	n_chained = __reduce_add_sync(0xffffffffu, n_chained);
-	if (lane == 0) {
-		ws.stats[0] += nq;
-		ws.stats[1] += n_leaf_hits;
-		ws.stats[2] += n_chained;
+	__syncwarp();
+	if (lane == 0)
 		ws.q_count = 0;
-	}
 	__syncwarp();
 }
 
-// Phase 1 for one lane's read: resumes at base *j0 with the rolling hashes of both strands and
-// returns when the longest read of the warp is done or the candidate queue is half full (the
-// caller drains it and calls again).  Four bases per iteration: one (unaligned) 32-bit shared
-// load, SIMD-in-register decode and validation, four roll steps; positions with a full h-base
-// window issue one filter probe (canonical h-mer) or, without a filter, two table probes.
-struct ScanCursor {
-	unsigned long long hf, hr;
-	uint32_t j0, bad4;
-};
-
-template <bool FILTER>
-__device__ __noinline__ void scanBases(const uint2 *__restrict__ filter, uint32_t filter_shift,
-		const TableSlot *__restrict__ table, uint64_t table_mask, uint32_t h, uint32_t debug_flags,
-		WarpState *wsp, uint32_t sbase, const uint8_t *gbase, bool staged, uint32_t rl, uint32_t wmax,
-		ScanCursor *cursor) {
-	WarpState &ws = *wsp;
-	const int lane = threadIdx.x & 31;
-	const unsigned long long pol_keep = policyEvictLast();
-	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
-	const uint32_t top_shift = 2 * h - 2;
-	unsigned long long hf = cursor->hf, hr = cursor->hr;
-	uint32_t j0 = cursor->j0, bad4 = cursor->bad4;
-	for (; j0 < wmax; j0 += kStepUnroll) {
-		// bytes j0..j0+3 of the read (garbage past rl is masked below)
-		uint32_t w4 = 0;
-		if (j0 < rl) {
-			if (staged) {
-				const uint32_t a = sbase + j0;
-				w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
-			} else {
-#pragma unroll
-				for (int u = 0; u < kStepUnroll; u++)
-					if (j0 + u < rl) w4 |= (uint32_t) gbase[j0 + u] << (8 * u);
-			}
-		}
-		// codes: A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
-		// letter the code stands for (one byte permute)
-		const uint32_t t4 = (w4 >> 1) & 0x03030303u;
-		const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-		const uint32_t nib = code4 | (code4 >> 4);
-		const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-		const uint32_t left = rl > j0 ? rl - j0 : 0u;
-		const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
-		bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
-
-		uint2 ff[kStepUnroll];                                // FILTER: filter words
-		uint32_t bsel[kStepUnroll];
-		unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: keys and table buckets
-		unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4];
-#pragma unroll
-		for (int u = 0; u < kStepUnroll; u++) {
-			const uint32_t j = j0 + u;
-			const uint32_t c = (code4 >> (8 * u)) & 3u;
-			hf = ((hf << 2) | c) & kmask;
-			hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
-			if (j + 1 >= h && j < rl) {
-				if (FILTER) {
-					// hr is the reverse complement of the window hf covers: ONE probe with the
-					// canonical h-mer answers both strands
-					uint32_t a;
-					filterHash(hf < hr ? hf : hr, a, bsel[u]);
-					// the two lowest bits of B are unused by the selectors: remember the orientation
-					bsel[u] = (bsel[u] & ~3u) | (hf <= hr ? 1u : 0u) | (hf == hr ? 2u : 0u);
-					if (debug_flags & 4u)
-						ff[u] = make_uint2(a, bsel[u]);
-					else
-						ff[u] = loadFilterWord(filter + filterWordIndex(a, filter_shift), pol_keep);
-				} else {
-					kf[u] = hf;
-					kr[u] = hr;
-					loadBucket(table + 2 * (mixKey(hf) & table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
-					loadBucket(table + 2 * (mixKey(hr) & table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
-				}
-			}
-		}
-		if (j0 + kStepUnroll >= h) { // warp-uniform: some step of this iteration has a full window
-#pragma unroll
-			for (int u = 0; u < kStepUnroll; u++) {
-				const uint32_t j = j0 + u;
-				bool cand_f = false, cand_r = false;
-				if (j + 1 >= h && j < rl) {
-					if (FILTER) {
-						// pattern of B: the canonical orientation is a key; other pattern: its reverse
-						// complement is.  fwd_canon says which strand holds the canonical orientation.
-						const bool same = filterTest(ff[u].x, ff[u].y, bsel[u]);
-						const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
-						const bool fwd_canon = (bsel[u] & 1u) != 0, palin = (bsel[u] & 2u) != 0;
-						cand_f = fwd_canon ? same : other;
-						cand_r = (fwd_canon && !palin) ? other : same;
-					} else {
-						// candidate = the bucket holds the key, or is full and the key may have spilled
-						cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
-						cand_r = br[u][0] == kr[u] || br[u][2] == kr[u] || (br[u][0] != kEmptyKey && br[u][2] != kEmptyKey);
-					}
-				}
-				if (cand_f) // forward strand, position i = j-h+1
-					ws.queue[atomicAdd(&ws.q_count, 1u)] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
-				if (cand_r) // reverse-complement strand: this window is rc position rl-1-j
-					ws.queue[atomicAdd(&ws.q_count, 1u)] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
-			}
-			__syncwarp();
-			// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: hand over above half
-			if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32)) {
-				j0 += kStepUnroll;
-				break;
-			}
-		}
-	}
-	cursor->hf = hf;
-	cursor->hr = hr;
-	cursor->j0 = j0;
-	cursor->bad4 = bad4;
-}
-
-// Phase 3 for one lane's read: leaf set -> decision (query.cpp:529-636 / 964-1067) -> rcount,
-// genome counters, optional per-read records.
-template <int MODE>
-__device__ __noinline__ void classifyRead(const ScanParams *pp, WarpState *wsp, uint32_t *smem_counts, const uint32_t *my_spill,
-		uint64_t r, bool have, bool valid) {
-	const ScanParams &p = *pp;
-	WarpState &ws = *wsp;
-	const int lane = threadIdx.x & 31;
-	const uint32_t G1 = p.n_genomes + 1;
-	uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;
-	const uint32_t nh = valid ? min((uint32_t) ws.hit_cnt[lane], (uint32_t) (kHitSeg + kHitSpill)) : 0;
-	if (nh > 0) {
-		uint32_t min_r = 0xFFFFFFFFu, max_r = 0;
-		unsigned long long min_p = ~0ull, max_p = 0;
-		for (uint32_t i = 0; i < nh; i++) {
-			uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
-			if (e & kRefLeafTag) {
-				uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
-				uint32_t l = min(ab.x, ab.y), g = max(ab.x, ab.y);
-				unsigned long long key = ((unsigned long long) l << 32) | g;
-				min_p = key < min_p ? key : min_p;
-				max_p = key > max_p ? key : max_p;
-			} else {
-				uint32_t rid = loadStreamU32(&p.leaf_u_ref[e]);
-				min_r = min(min_r, rid);
-				max_r = max(max_r, rid);
-			}
-		}
-		const int nr = (min_r == 0xFFFFFFFFu) ? 0 : (min_r == max_r ? 1 : 2);
-		const int np = (min_p == ~0ull) ? 0 : (min_p == max_p ? 1 : 2);
-		const uint32_t a0 = (uint32_t) (min_p >> 32), b0 = (uint32_t) min_p;
-		if (np == 0) {
-			if (nr == 1) { cls = CQ_CLASS_U; rid_a = min_r; }
-			else cls = CQ_CLASS_CONFLICT;
-		} else if (np == 1) {
-			if (nr == 0) { cls = CQ_CLASS_D_PAIR; rid_a = a0; rid_b = b0; }
-			else if (nr == 2) cls = CQ_CLASS_CONFLICT;
-			else if (a0 != min_r && b0 != min_r) cls = CQ_CLASS_CONFLICT;
-			else { cls = CQ_CLASS_UD; rid_a = min_r; }
-		} else if (nr == 2) {
-			cls = CQ_CLASS_CONFLICT;
-		} else {
-			// |P| >= 2: does every pair contain r (|R| == 1), or which of a0 / b0 lies in
-			// every pair (|R| == 0, the intersection of query.cpp:604-633)
-			bool all_a = true, all_b = true;
-			const uint32_t ta = nr == 1 ? min_r : a0, tb = nr == 1 ? min_r : b0;
-			for (uint32_t i = 0; i < nh; i++) {
-				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
-				if (e & kRefLeafTag) {
-					uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
-					all_a &= (ab.x == ta || ab.y == ta);
-					all_b &= (ab.x == tb || ab.y == tb);
-				}
-			}
-			if (nr == 1) {
-				if (all_a) { cls = CQ_CLASS_UD; rid_a = min_r; }
-				else cls = CQ_CLASS_CONFLICT;
-			} else {
-				int ni = (all_a ? 1 : 0) + ((b0 != a0 && all_b) ? 1 : 0);
-				if (ni == 1) { cls = CQ_CLASS_D_INTER; rid_a = all_a ? a0 : b0; }
-				else cls = CQ_CLASS_CONFLICT;
-			}
-		}
-		// distinct leaves: rcount += 1 per distinct leaf of an accepted read (query.cpp:550-551)
-		const bool accepted = cls >= CQ_CLASS_U;
-		const bool want_sets = p.read_nleaf_u != NULL;
-		if ((MODE == CQ_MODE_P && accepted) || want_sets) {
-			const unsigned long long pol_stream = policyEvictFirst();
-			for (uint32_t i = 0; i < nh; i++) {
-				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
-				bool first = true;
-				for (uint32_t q = 0; q < i && first; q++)
-					first = (q < (uint32_t) kHitSeg ? ws.hits[lane][q] : my_spill[q - kHitSeg]) != e;
-				if (!first)
-					continue;
-				const bool is_d = (e & kRefLeafTag) != 0;
-				const uint32_t leaf = e & ~kRefLeafTag;
-				if (MODE == CQ_MODE_P && accepted)
-					redAddStream(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], pol_stream);
-				if (want_sets) {
-					uint32_t at = is_d ? distinct_d : distinct_u;
-					if (at < p.leaf_cap)
-						(is_d ? p.read_leaf_d : p.read_leaf_u)[r * p.leaf_cap + at] = leaf;
-				}
-				if (is_d) distinct_d++;
-				else distinct_u++;
-			}
-		}
-	}
-
-	// ---- counters (the effects of query.cpp:542-636) ---------------------------------------------
-	if (have) {
-		const bool inc_u = cls == CQ_CLASS_U || cls == CQ_CLASS_UD || (cls == CQ_CLASS_D_INTER && MODE == CQ_MODE_SC);
-		const bool inc_d = cls >= CQ_CLASS_D_PAIR;
-		if (cls >= CQ_CLASS_U) {
-			if (p.smem_counters) {
-				if (inc_u) atomicAdd(&smem_counts[rid_a], 1u);
-				if (inc_d) atomicAdd(&smem_counts[G1 + rid_a], 1u);
-				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&smem_counts[G1 + rid_b], 1u);
-			} else {
-				if (inc_u) atomicAdd(&p.counts[rid_a], 1ull);
-				if (inc_d) atomicAdd(&p.counts[G1 + rid_a], 1ull);
-				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&p.counts[G1 + rid_b], 1ull);
-			}
-		}
-		if (MODE == CQ_MODE_SC && cls == CQ_CLASS_D_PAIR) {
-			unsigned long long at = atomicAdd(&p.counts[2 * G1 + 3], 1ull);
-			p.pair_records[at] = ((unsigned long long) rid_a << 32) | rid_b;
-		}
-		if (p.read_class) {
-			p.read_class[r] = (uint8_t) cls;
-			p.read_rid_a[r] = rid_a;
-			p.read_rid_b[r] = rid_b;
-		}
-		if (p.read_nleaf_u) {
-			p.read_nleaf_u[r] = distinct_u;
-			p.read_nleaf_d[r] = distinct_d;
-		}
-	}
-	const uint32_t m_und = __ballot_sync(0xffffffffu, have && cls == CQ_CLASS_UNLABELED);
-	const uint32_t m_conf = __ballot_sync(0xffffffffu, have && cls == CQ_CLASS_CONFLICT);
-	const uint32_t m_inv = __ballot_sync(0xffffffffu, have && !valid);
-	if (lane == 0) {
-		ws.tally[0] += __popc(m_und);
-		ws.tally[1] += __popc(m_conf);
-		ws.tally[2] += __popc(m_inv);
-	}
+__device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
 }
 
 template <int MODE, bool FILTER>
-__global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams p) {
 	// [8 warps][tile_cap bytes of ASCII] | [2*(G+1) u32 genome counters]
 	extern __shared__ __align__(128) uint8_t dyn_smem[];
 	__shared__ __align__(16) WarpState warp_state[kWarpsPerBlock];
@@ -564,7 +293,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(const __gri
 
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * p.tile_cap);
-	const uint32_t ncnt = 2 * (p.n_genomes + 1);
+	const uint32_t G1 = p.n_genomes + 1, ncnt = 2 * G1;
 	if (p.smem_counters)
 		for (uint32_t i = tid; i < ncnt; i += blockDim.x)
 			smem_counts[i] = 0;
@@ -573,17 +302,19 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(const __gri
 	WarpState &ws = warp_state[wib];
 	if (lane == 0) {
 		ws.q_count = 0;
-		ws.stats[0] = ws.stats[1] = ws.stats[2] = ws.stats[3] = 0;
-		ws.tally[0] = ws.tally[1] = ws.tally[2] = 0;
 		mbarInit(&ws.bar, 1);
 	}
 	__syncthreads();
 
 	const uint32_t h = p.h;
+	const unsigned long long pol_keep = policyEvictLast(), pol_stream = policyEvictFirst();
+	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
+	const uint32_t top_shift = 2 * h - 2;
 	uint8_t *wbuf = dyn_smem + (size_t) wib * p.tile_cap;
 	uint32_t *warp_spill = p.hit_spill + ((size_t) blockIdx.x * kWarpsPerBlock + wib) * 32 * kHitSpill;
+	unsigned long long n_undet = 0, n_conf = 0, n_invalid = 0;
+	uint32_t n_probes = 0, n_cand = 0, n_leaf_hits = 0, n_chained = 0; // per lane
 	uint32_t parity = 0;
-	unsigned long long n_probes = 0; // per lane
 
 	// Every warp owns sub-tiles of 32 reads (one read per lane) and streams them through its own
 	// staging buffer with its own mbarrier: no block-wide barrier in the loop, the other warps
@@ -592,95 +323,313 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(const __gri
 	const uint64_t warp_stride = (uint64_t) gridDim.x * kWarpsPerBlock;
 	uint64_t sub = (uint64_t) blockIdx.x * kWarpsPerBlock + wib;
 
-	// this lane's read of the next sub-tile: offset and length (loaded one sub-tile ahead)
-	unsigned long long nxt_off = ~0ull;
-	uint32_t nxt_rl = 0;
-	if (sub < n_sub) {
-		const uint64_t r0 = sub * 32 + lane;
-		if (r0 < p.n_reads) {
-			nxt_off = p.offsets ? p.offsets[r0] : (p.read_base + r0) * p.stride;
-			nxt_rl = p.lengths[r0];
-		}
-	}
-
-	for (; sub < n_sub; sub += warp_stride) {
-		const uint64_t r = sub * 32 + lane;
-		const bool have = r < p.n_reads;
-		const unsigned long long off = nxt_off;
-		const uint32_t rl = nxt_rl;
-		// ---- stage: one TMA bulk copy of the byte span the 32 reads cover ---------------------------
-		unsigned long long lo = off, hi = have ? off + rl : 0ull;
+	struct SubTile {
+		unsigned long long off, start; // this lane's read offset; 16-byte aligned start of the span
+		uint32_t rl, bytes;
+		bool have, staged;
+	};
+	// offsets / lengths of a sub-tile's reads and the byte span they cover (warp-uniform)
+	auto describe = [&](uint64_t sub_idx) -> SubTile {
+		SubTile t;
+		const uint64_t r = sub_idx * 32 + lane;
+		t.have = r < p.n_reads;
+		t.off = t.have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
+		t.rl = t.have ? p.lengths[r] : 0;
+		unsigned long long lo = t.off, hi = t.have ? t.off + t.rl : 0ull;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			unsigned long long tl = __shfl_xor_sync(0xffffffffu, lo, o), th = __shfl_xor_sync(0xffffffffu, hi, o);
 			lo = tl < lo ? tl : lo;
 			hi = th > hi ? th : hi;
 		}
-		const unsigned long long start = lo & ~15ull;
-		const unsigned long long span = hi > start ? ((hi - start + 15ull) & ~15ull) : 0ull;
-		const bool staged = span > 0 && span <= p.tile_cap; // else: the reads are fetched from global directly
-		if (staged && lane == 0) {
-			mbarExpectTx(&ws.bar, (uint32_t) span);
-			bulkCopyG2S(wbuf, p.bases + start, (uint32_t) span, &ws.bar, policyEvictFirst());
-		}
-		// next sub-tile's offsets / lengths: in flight while this one is scanned
-		nxt_off = ~0ull;
-		nxt_rl = 0;
-		if (sub + warp_stride < n_sub) {
-			const uint64_t rn = (sub + warp_stride) * 32 + lane;
-			if (rn < p.n_reads) {
-				nxt_off = p.offsets ? p.offsets[rn] : (p.read_base + rn) * p.stride;
-				nxt_rl = p.lengths[rn];
+		t.start = lo & ~15ull;
+		t.bytes = hi > t.start ? (uint32_t) min((hi - t.start + 15ull) & ~15ull, 0xFFFFFFF0ull) : 0u;
+		t.staged = t.bytes > 0 && t.bytes <= p.tile_cap; // else: the reads are fetched from global directly
+		return t;
+	};
+
+	SubTile cur;
+	cur.have = false; cur.staged = false; cur.rl = 0; cur.off = 0; cur.start = 0; cur.bytes = 0;
+	if (sub < n_sub)
+		cur = describe(sub);
+	for (; sub < n_sub; sub += warp_stride) {
+		// one TMA bulk copy brings the sub-tile's ASCII bytes into the warp's buffer
+		if (cur.staged) {
+			if (lane == 0) {
+				mbarExpectTx(&ws.bar, cur.bytes);
+				bulkCopyG2S(wbuf, p.bases + cur.start, cur.bytes, &ws.bar, pol_stream);
 			}
 		}
-		const uint32_t soff = staged && have ? (uint32_t) (off - start) : 0u;
+		// the next sub-tile's offsets / lengths are fetched while this one is in flight
+		SubTile nxt;
+		nxt.have = false; nxt.staged = false; nxt.rl = 0; nxt.off = 0; nxt.start = 0; nxt.bytes = 0;
+		if (sub + warp_stride < n_sub)
+			nxt = describe(sub + warp_stride);
+		if (cur.staged) {
+			mbarWait(&ws.bar, parity);
+			parity ^= 1u;
+		}
+		const uint64_t r = sub * 32 + lane;
+		const bool have = cur.have, staged = cur.staged;
+		const uint32_t rl = cur.rl;
+		const uint8_t *tbuf = wbuf;
+		const uint32_t soff = staged && have ? (uint32_t) (cur.off - cur.start) : 0u;
 		ws.soff[lane] = soff;
-		ws.goff[lane] = have ? off : 0ull;
+		ws.goff[lane] = have ? cur.off : 0ull;
 		ws.rl[lane] = (uint8_t) rl;
 		ws.hit_cnt[lane] = 0;
 		if (lane == 0)
 			ws.staged = staged ? 1u : 0u;
-		if (staged) {
-			mbarWait(&ws.bar, parity);
-			parity ^= 1u;
-		}
 		__syncwarp();
 
-		// ---- phase 1 (probe loop) alternating with phase 2 (queue drain) --------------------------
-		ScanCursor cur;
-		cur.hf = cur.hr = 0;
-		cur.j0 = cur.bad4 = 0;
+		// ---- phase 1: thread per read, rolling hashes of both strands, filter / table test ------
+		// Four bases per iteration: one (unaligned) 32-bit shared load, SIMD-in-register decode
+		// and validation, then four roll steps; positions with a full h-base window are probed.
+		const uint32_t sbase = smemAddr(tbuf) + soff;
+		const uint8_t *gbase = p.bases + (have ? cur.off : 0ull);
+		uint32_t bad4 = 0;
+		unsigned long long hf = 0, hr = 0;
 		const uint32_t wmax = __reduce_max_sync(0xffffffffu, rl);
-		do {
-			scanBases<FILTER>(p.filter, p.filter_shift, p.table, p.table_mask, h, p.debug_flags, &ws,
-				smemAddr(wbuf) + soff, p.bases + (have ? off : 0ull), staged, rl, wmax, &cur);
-			if (!(p.debug_flags & 2u))
-				drainQueue(&p, &ws, wbuf, warp_spill);
-			else if (lane == 0)
-				ws.q_count = 0;
-			__syncwarp();
-		} while (cur.j0 < wmax);
+		for (uint32_t j0 = 0; j0 < wmax; j0 += kStepUnroll) {
+			// bytes j0..j0+3 of the read (garbage past rl is masked below)
+			uint32_t w4 = 0;
+			if (j0 < rl) {
+				if (staged) {
+					const uint32_t a = sbase + j0;
+					w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
+				} else {
+#pragma unroll
+					for (int u = 0; u < kStepUnroll; u++)
+						if (j0 + u < rl) w4 |= (uint32_t) gbase[j0 + u] << (8 * u);
+				}
+			}
+			// codes: A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
+			// letter the code stands for (one byte permute)
+			const uint32_t t4 = (w4 >> 1) & 0x03030303u;
+			const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+			const uint32_t nib = code4 | (code4 >> 4);
+			const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+			const uint32_t left = rl > j0 ? rl - j0 : 0u;
+			const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
+			bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
 
-		// ---- phase 3 -----------------------------------------------------------------------------------
-		const bool valid = have && cur.bad4 == 0 && rl >= h;
-		if (valid)
-			n_probes += 2 * (rl - h + 1);
-		classifyRead<MODE>(&p, &ws, smem_counts, warp_spill + (size_t) lane * kHitSpill, r, have, valid);
-		__syncwarp(); // every lane is done with the staging buffer and the warp state
+			uint2 ff[kStepUnroll];                                // FILTER: filter words
+			uint32_t bsel[kStepUnroll];
+			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: keys and table buckets
+			unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4];
+#pragma unroll
+			for (int u = 0; u < kStepUnroll; u++) {
+				const uint32_t j = j0 + u;
+				const uint32_t c = (code4 >> (8 * u)) & 3u;
+				hf = ((hf << 2) | c) & kmask;
+				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
+				if (j + 1 >= h && j < rl) {
+					if (FILTER) {
+						// hr is the reverse complement of the window hf covers: ONE probe with the
+						// canonical h-mer answers both strands
+						uint32_t a;
+						filterHash(hf < hr ? hf : hr, a, bsel[u]);
+						// the two lowest bits of B are unused by the selectors: remember the orientation
+						bsel[u] = (bsel[u] & ~3u) | (hf <= hr ? 1u : 0u) | (hf == hr ? 2u : 0u);
+						if (p.debug_flags & 4u)
+							ff[u] = make_uint2(a, bsel[u]);
+						else
+							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_shift), pol_keep);
+					} else {
+						kf[u] = hf;
+						kr[u] = hr;
+						loadBucket(p.table + 2 * (mixKey(hf) & p.table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
+						loadBucket(p.table + 2 * (mixKey(hr) & p.table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
+					}
+				}
+			}
+			if (j0 + kStepUnroll >= h) { // warp-uniform: some step of this iteration has a full window
+#pragma unroll
+				for (int u = 0; u < kStepUnroll; u++) {
+					const uint32_t j = j0 + u;
+					bool cand_f = false, cand_r = false;
+					if (j + 1 >= h && j < rl) {
+						n_probes += 2;
+						if (FILTER) {
+							// pattern of B: the canonical orientation is a key; other pattern: its reverse
+							// complement is.  fwd_canon says which strand holds the canonical orientation.
+							const bool same = filterTest(ff[u].x, ff[u].y, bsel[u]);
+							const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
+							const bool fwd_canon = (bsel[u] & 1u) != 0, palin = (bsel[u] & 2u) != 0;
+							cand_f = fwd_canon ? same : other;
+							cand_r = (fwd_canon && !palin) ? other : same;
+						} else {
+							// candidate = the bucket holds the key, or is full and the key may have spilled
+							cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
+							cand_r = br[u][0] == kr[u] || br[u][2] == kr[u] || (br[u][0] != kEmptyKey && br[u][2] != kEmptyKey);
+						}
+					}
+					if (p.debug_flags & 2u) {
+						n_cand += cand_f + cand_r;
+						cand_f = cand_r = false;
+					}
+					if (cand_f) {
+						// forward strand, position i = j-h+1
+						uint32_t at = atomicAdd(&ws.q_count, 1u);
+						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
+						n_cand++;
+					}
+					if (cand_r) {
+						// reverse-complement strand: this window is rc position rl-1-j
+						uint32_t at = atomicAdd(&ws.q_count, 1u);
+						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
+						n_cand++;
+					}
+				}
+				__syncwarp();
+				// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
+				if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
+					drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+			}
+		}
+		const bool bad = bad4 != 0;
+		drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+
+		// ---- phase 3: thread per read: leaf set -> decision (query.cpp:529-636) ------------------
+		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;
+		const bool valid = have && !bad && rl >= h;
+		const uint32_t nh = valid ? min((uint32_t) ws.hit_cnt[lane], (uint32_t) (kHitSeg + kHitSpill)) : 0;
+		const uint32_t *my_spill = warp_spill + (size_t) lane * kHitSpill;
+		if (nh > 0) {
+			uint32_t min_r = 0xFFFFFFFFu, max_r = 0;
+			unsigned long long min_p = ~0ull, max_p = 0;
+			for (uint32_t i = 0; i < nh; i++) {
+				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
+				if (e & kRefLeafTag) {
+					uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
+					uint32_t l = min(ab.x, ab.y), g = max(ab.x, ab.y);
+					unsigned long long key = ((unsigned long long) l << 32) | g;
+					min_p = key < min_p ? key : min_p;
+					max_p = key > max_p ? key : max_p;
+				} else {
+					uint32_t rid = loadStreamU32(&p.leaf_u_ref[e]);
+					min_r = min(min_r, rid);
+					max_r = max(max_r, rid);
+				}
+			}
+			const int nr = (min_r == 0xFFFFFFFFu) ? 0 : (min_r == max_r ? 1 : 2);
+			const int np = (min_p == ~0ull) ? 0 : (min_p == max_p ? 1 : 2);
+			const uint32_t a0 = (uint32_t) (min_p >> 32), b0 = (uint32_t) min_p;
+			if (np == 0) {
+				if (nr == 1) { cls = CQ_CLASS_U; rid_a = min_r; }
+				else cls = CQ_CLASS_CONFLICT;
+			} else if (np == 1) {
+				if (nr == 0) { cls = CQ_CLASS_D_PAIR; rid_a = a0; rid_b = b0; }
+				else if (nr == 2) cls = CQ_CLASS_CONFLICT;
+				else if (a0 != min_r && b0 != min_r) cls = CQ_CLASS_CONFLICT;
+				else { cls = CQ_CLASS_UD; rid_a = min_r; }
+			} else if (nr == 2) {
+				cls = CQ_CLASS_CONFLICT;
+			} else {
+				// |P| >= 2: does every pair contain r (|R| == 1), or which of a0 / b0 lies in
+				// every pair (|R| == 0, the intersection of query.cpp:604-633)
+				bool all_a = true, all_b = true;
+				const uint32_t ta = nr == 1 ? min_r : a0, tb = nr == 1 ? min_r : b0;
+				for (uint32_t i = 0; i < nh; i++) {
+					uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
+					if (e & kRefLeafTag) {
+						uint2 ab = loadStreamU32x2(&p.leaf_d_ref[e & ~kRefLeafTag]);
+						all_a &= (ab.x == ta || ab.y == ta);
+						all_b &= (ab.x == tb || ab.y == tb);
+					}
+				}
+				if (nr == 1) {
+					if (all_a) { cls = CQ_CLASS_UD; rid_a = min_r; }
+					else cls = CQ_CLASS_CONFLICT;
+				} else {
+					int ni = (all_a ? 1 : 0) + ((b0 != a0 && all_b) ? 1 : 0);
+					if (ni == 1) { cls = CQ_CLASS_D_INTER; rid_a = all_a ? a0 : b0; }
+					else cls = CQ_CLASS_CONFLICT;
+				}
+			}
+			// distinct leaves: rcount += 1 per distinct leaf of an accepted read (query.cpp:550-551)
+			const bool accepted = cls >= CQ_CLASS_U;
+			const bool want_sets = p.read_nleaf_u != NULL;
+			if ((MODE == CQ_MODE_P && accepted) || want_sets) {
+				for (uint32_t i = 0; i < nh; i++) {
+					uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
+					bool first = true;
+					for (uint32_t q = 0; q < i && first; q++)
+						first = (q < (uint32_t) kHitSeg ? ws.hits[lane][q] : my_spill[q - kHitSeg]) != e;
+					if (!first)
+						continue;
+					const bool is_d = (e & kRefLeafTag) != 0;
+					const uint32_t leaf = e & ~kRefLeafTag;
+					if (MODE == CQ_MODE_P && accepted)
+						redAddStream(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], pol_stream);
+					if (want_sets) {
+						uint32_t at = is_d ? distinct_d : distinct_u;
+						if (at < p.leaf_cap)
+							(is_d ? p.read_leaf_d : p.read_leaf_u)[r * p.leaf_cap + at] = leaf;
+					}
+					if (is_d) distinct_d++;
+					else distinct_u++;
+				}
+			}
+		}
+
+		// ---- counters (the effects of query.cpp:542-636) ---------------------------------------------
+		if (have) {
+			const bool inc_u = cls == CQ_CLASS_U || cls == CQ_CLASS_UD || (cls == CQ_CLASS_D_INTER && MODE == CQ_MODE_SC);
+			const bool inc_d = cls >= CQ_CLASS_D_PAIR;
+			if (!valid) n_invalid++;
+			if (cls == CQ_CLASS_UNLABELED) n_undet++;
+			else if (cls == CQ_CLASS_CONFLICT) n_conf++;
+			else if (p.smem_counters) {
+				if (inc_u) atomicAdd(&smem_counts[rid_a], 1u);
+				if (inc_d) atomicAdd(&smem_counts[G1 + rid_a], 1u);
+				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&smem_counts[G1 + rid_b], 1u);
+			} else {
+				if (inc_u) atomicAdd(&p.counts[rid_a], 1ull);
+				if (inc_d) atomicAdd(&p.counts[G1 + rid_a], 1ull);
+				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&p.counts[G1 + rid_b], 1ull);
+			}
+			if (MODE == CQ_MODE_SC && cls == CQ_CLASS_D_PAIR) {
+				unsigned long long at = atomicAdd(&p.counts[2 * G1 + 3], 1ull);
+				p.pair_records[at] = ((unsigned long long) rid_a << 32) | rid_b;
+			}
+			if (p.read_class) {
+				p.read_class[r] = (uint8_t) cls;
+				p.read_rid_a[r] = rid_a;
+				p.read_rid_b[r] = rid_b;
+			}
+			if (p.read_nleaf_u) {
+				p.read_nleaf_u[r] = distinct_u;
+				p.read_nleaf_d[r] = distinct_d;
+			}
+		}
+		__syncwarp(); // every lane is done with this staging buffer and the warp state
+		cur = nxt;
 	}
 
 	// ---- block totals ---------------------------------------------------------------------------------
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+	for (int o = 16; o > 0; o >>= 1) {
+		n_undet += __shfl_xor_sync(0xffffffffu, n_undet, o);
+		n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+		n_invalid += __shfl_xor_sync(0xffffffffu, n_invalid, o);
+	}
+	unsigned long long probes64 = n_probes, cand64 = n_cand, leaf64 = n_leaf_hits, chain64 = n_chained;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		probes64 += __shfl_xor_sync(0xffffffffu, probes64, o);
+		cand64 += __shfl_xor_sync(0xffffffffu, cand64, o);
+		leaf64 += __shfl_xor_sync(0xffffffffu, leaf64, o);
+		chain64 += __shfl_xor_sync(0xffffffffu, chain64, o);
+	}
 	if (lane == 0) {
-		if (ws.tally[0]) atomicAdd(&block_tot[0], (unsigned long long) ws.tally[0]);
-		if (ws.tally[1]) atomicAdd(&block_tot[1], (unsigned long long) ws.tally[1]);
-		if (ws.tally[2]) atomicAdd(&p.counts[ncnt + 2], (unsigned long long) ws.tally[2]);
-		if (n_probes) atomicAdd(&p.probe_count[0], n_probes);
-		if (ws.stats[0]) atomicAdd(&p.probe_count[1], (unsigned long long) ws.stats[0]);
-		if (ws.stats[1]) atomicAdd(&p.probe_count[2], (unsigned long long) ws.stats[1]);
-		if (ws.stats[2]) atomicAdd(&p.probe_count[3], (unsigned long long) ws.stats[2]);
+		if (n_undet) atomicAdd(&block_tot[0], n_undet);
+		if (n_conf) atomicAdd(&block_tot[1], n_conf);
+		if (n_invalid) atomicAdd(&p.counts[ncnt + 2], n_invalid);
+		if (probes64) atomicAdd(&p.probe_count[0], probes64);
+		if (cand64) atomicAdd(&p.probe_count[1], cand64);
+		if (leaf64) atomicAdd(&p.probe_count[2], leaf64);
+		if (chain64) atomicAdd(&p.probe_count[3], chain64);
 	}
 	__syncthreads();
 	if (p.smem_counters) {
