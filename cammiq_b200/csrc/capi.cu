@@ -94,7 +94,8 @@ struct cq_ctx {
 	uint8_t *d_read_class = NULL;
 	uint32_t *d_read_rid_a = NULL, *d_read_rid_b = NULL, *d_nleaf_u = NULL, *d_nleaf_d = NULL,
 		*d_leaf_u = NULL, *d_leaf_d = NULL;
-	size_t cap_per_read = 0, cap_leaf_lists = 0;
+	size_t cap_read_class = 0, cap_read_rid_a = 0, cap_read_rid_b = 0, cap_nleaf_u = 0, cap_nleaf_d = 0,
+		cap_leaf_u = 0, cap_leaf_d = 0;
 	uint32_t leaf_cap = 0;
 	bool want_per_read = false, want_sets = false;
 	cq_timing timing;
@@ -579,17 +580,15 @@ static int prepareOutputs(cq_ctx *c, int mode, uint64_t n) {
 		}
 	}
 	if (c->want_per_read) {
-		size_t cap2 = 0;
-		cap2 = 0; if ((rc = ensure(&c->d_read_class, &cap2, (size_t) n)) != 0) return rc;
-		cap2 = 0; if ((rc = ensure(&c->d_read_rid_a, &cap2, (size_t) n)) != 0) return rc;
-		cap2 = 0; if ((rc = ensure(&c->d_read_rid_b, &cap2, (size_t) n)) != 0) return rc;
+		if ((rc = ensure(&c->d_read_class, &c->cap_read_class, (size_t) n)) != 0) return rc;
+		if ((rc = ensure(&c->d_read_rid_a, &c->cap_read_rid_a, (size_t) n)) != 0) return rc;
+		if ((rc = ensure(&c->d_read_rid_b, &c->cap_read_rid_b, (size_t) n)) != 0) return rc;
 	}
 	if (c->want_sets) {
-		size_t cap2 = 0;
-		cap2 = 0; if ((rc = ensure(&c->d_nleaf_u, &cap2, (size_t) n)) != 0) return rc;
-		cap2 = 0; if ((rc = ensure(&c->d_nleaf_d, &cap2, (size_t) n)) != 0) return rc;
-		cap2 = 0; if ((rc = ensure(&c->d_leaf_u, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
-		cap2 = 0; if ((rc = ensure(&c->d_leaf_d, &cap2, (size_t) n * c->leaf_cap)) != 0) return rc;
+		if ((rc = ensure(&c->d_nleaf_u, &c->cap_nleaf_u, (size_t) n)) != 0) return rc;
+		if ((rc = ensure(&c->d_nleaf_d, &c->cap_nleaf_d, (size_t) n)) != 0) return rc;
+		if ((rc = ensure(&c->d_leaf_u, &c->cap_leaf_u, (size_t) n * c->leaf_cap)) != 0) return rc;
+		if ((rc = ensure(&c->d_leaf_d, &c->cap_leaf_d, (size_t) n * c->leaf_cap)) != 0) return rc;
 		CQ_CUDA(cudaMemsetAsync(c->d_leaf_u, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 		CQ_CUDA(cudaMemsetAsync(c->d_leaf_d, 0, std::max<size_t>((size_t) n * c->leaf_cap, 1) * 4, c->stream));
 	}

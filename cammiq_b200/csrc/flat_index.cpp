@@ -1,6 +1,12 @@
 #include "flat_index.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <new>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 
 #include "../../include/cammiq_gpu.h"
 
@@ -13,8 +19,13 @@ uint64_t FlatIndex::deviceBytes() const {
 
 namespace {
 
+unsigned flattenThreads() {
+	unsigned n = std::thread::hardware_concurrency();
+	return std::max(1u, std::min(n, 16u));
+}
+
 // Insert (or find) key; returns the slot.  Linear probing by bucket.
-inline TableSlot *probeInsert(std::vector<TableSlot> &t, uint64_t mask, uint64_t key, bool &fresh) {
+inline TableSlot *probeInsert(RawArray<TableSlot> &t, uint64_t mask, uint64_t key, bool &fresh) {
 	uint64_t b = mixKey(key) & mask;
 	for (;;) {
 		TableSlot *s = &t[b * kSlotsPerBucket];
@@ -54,32 +65,105 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 	while (nb < want)
 		nb <<= 1;
 	out.n_table_buckets = nb;
-	TableSlot empty = {kEmptyKey, kRefNone, kRefNone};
-	out.table.assign(nb * kSlotsPerBucket, empty);
-	uint64_t mask = nb - 1, n_keys = 0;
+	// the table is a few GB: allocate it raw and first-touch it from all threads
+	if (!out.table.alloc(nb * kSlotsPerBucket))
+		throw std::bad_alloc();
+	{
+		const TableSlot empty = {kEmptyKey, kRefNone, kRefNone};
+		const unsigned Ti = flattenThreads();
+		std::vector<std::thread> pool;
+		for (unsigned p = 0; p < Ti; p++)
+			pool.emplace_back([&, p]() {
+				const size_t lo = out.table.size() * p / Ti, hi = out.table.size() * (p + 1) / Ti;
+				for (size_t i = lo; i < hi; i++)
+					out.table[i] = empty;
+			});
+		for (auto &th : pool) th.join();
+	}
+	if (getenv("CAMMIQ_VERBOSE")) fprintf(stderr, "[flatten] table init %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
+	const uint64_t mask = nb - 1;
 	const uint64_t key_limit = (u.hash_len >= 32) ? UINT64_MAX : (1ull << (2 * u.hash_len));
-	for (int t = 0; t < 2; t++) {
-		DecodedIndex &x = t == 0 ? u : d;
-		for (size_t i = 0; i < x.bucket_key.size(); i++) {
-			uint64_t key = x.bucket_key[i];
-			if (key >= key_limit) {
-				err = "Bucket key does not fit 2*hash_len bits.";
-				return CQ_EFORMAT;
-			}
+	// Parallel build: thread p owns the home buckets [nb*p/T, nb*(p+1)/T) and inserts, in file
+	// order, exactly the keys whose home bucket lies there, probing inside its own range; the
+	// few keys whose probe sequence would cross the range end are inserted afterwards by one
+	// thread.  Every key stored past its home bucket still has only full buckets before it, so
+	// lookups (stop at the first bucket with a free slot) are unaffected.
+	const unsigned T = flattenThreads();
+	struct Deferred { uint8_t table; uint64_t index; };
+	std::vector<std::vector<Deferred>> deferred(T);
+	std::vector<uint64_t> fresh_keys(T, 0);
+	std::atomic<bool> bad_key(false);
+	{
+		std::vector<std::thread> pool;
+		for (unsigned p = 0; p < T; p++)
+			pool.emplace_back([&, p]() {
+				const uint64_t lo = nb * p / T, hi = nb * (p + 1) / T;
+				for (int t = 0; t < 2; t++) {
+					const DecodedIndex &x = t == 0 ? u : d;
+					for (size_t i = 0; i < x.bucket_key.size(); i++) {
+						const uint64_t key = x.bucket_key[i];
+						uint64_t b = mixKey(key) & mask;
+						if (b < lo || b >= hi)
+							continue;
+						if (key >= key_limit) {
+							bad_key = true;
+							continue;
+						}
+						TableSlot *hit = NULL;
+						for (; b < hi && hit == NULL; b++) {
+							TableSlot *s = &out.table[b * kSlotsPerBucket];
+							for (int k = 0; k < kSlotsPerBucket; k++) {
+								if (s[k].key == key) {
+									hit = &s[k];
+									break;
+								}
+								if (s[k].key == kEmptyKey) {
+									s[k].key = key;
+									fresh_keys[p]++;
+									hit = &s[k];
+									break;
+								}
+							}
+						}
+						if (hit == NULL) {
+							Deferred df = {(uint8_t) t, (uint64_t) i};
+							deferred[p].push_back(df);
+							continue;
+						}
+						// a repeated key inside one file: the later bucket replaces the earlier one, as
+						// map64[bucket] = root does (hashtrie.cpp:500)
+						if (t == 0)
+							hit->u_ref = x.bucket_root[i];
+						else
+							hit->d_ref = x.bucket_root[i];
+					}
+				}
+			});
+		for (auto &th : pool) th.join();
+	}
+	if (getenv("CAMMIQ_VERBOSE")) fprintf(stderr, "[flatten] parallel insert done %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
+	if (bad_key) {
+		err = "Bucket key does not fit 2*hash_len bits.";
+		return CQ_EFORMAT;
+	}
+	uint64_t n_keys = 0;
+	for (unsigned p = 0; p < T; p++) {
+		n_keys += fresh_keys[p];
+		for (const Deferred &df : deferred[p]) {
+			const DecodedIndex &x = df.table == 0 ? u : d;
 			bool fresh;
-			TableSlot *s = probeInsert(out.table, mask, key, fresh);
+			TableSlot *s = probeInsert(out.table, mask, x.bucket_key[df.index], fresh);
 			n_keys += fresh ? 1 : 0;
-			// a repeated key inside one file: the later bucket replaces the earlier one, as
-			// map64[bucket] = root does (hashtrie.cpp:500)
-			if (t == 0)
-				s->u_ref = x.bucket_root[i];
+			if (df.table == 0)
+				s->u_ref = x.bucket_root[df.index];
 			else
-				s->d_ref = x.bucket_root[i];
+				s->d_ref = x.bucket_root[df.index];
 		}
 	}
 	out.n_keys = n_keys;
 	out.u = std::move(u);
 	out.d = std::move(d);
+	if (getenv("CAMMIQ_VERBOSE")) fprintf(stderr, "[flatten] before filter %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count());
 	buildFilter(out, kFilterMaxBytesDefault);
 	out.flatten_ms = std::chrono::duration<double, std::milli>(
 		std::chrono::high_resolution_clock::now() - t0).count();
@@ -102,14 +186,22 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 	while ((1ull << bits) < words)
 		bits++;
 	fi.filter_shift = 32 - bits;
-	for (size_t i = 0; i < fi.table.size(); i++) {
-		if (fi.table[i].key == kEmptyKey)
-			continue;
-		uint32_t A, B;
-		const uint64_t key = fi.table[i].key, canon = canonicalKeyHost(key, fi.hash_len);
-		filterHash(canon, A, B);
-		fi.filter[filterWordIndex(A, fi.filter_shift)] |= filterMask(key == canon ? B : filterOtherPattern(B));
-	}
+	const unsigned T = flattenThreads();
+	std::vector<std::thread> pool;
+	for (unsigned p = 0; p < T; p++)
+		pool.emplace_back([&, p]() {
+			const size_t lo = fi.table.size() * p / T, hi = fi.table.size() * (p + 1) / T;
+			for (size_t i = lo; i < hi; i++) {
+				if (fi.table[i].key == kEmptyKey)
+					continue;
+				uint32_t A, B;
+				const uint64_t key = fi.table[i].key, canon = canonicalKeyHost(key, fi.hash_len);
+				filterHash(canon, A, B);
+				__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_shift)],
+					filterMask(key == canon ? B : filterOtherPattern(B)), __ATOMIC_RELAXED);
+			}
+		});
+	for (auto &th : pool) th.join();
 }
 
 uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t *cand, size_t len) {

@@ -14,6 +14,7 @@
 #define CAMMIQ_FLAT_INDEX_HPP
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -54,7 +55,7 @@ inline uint64_t mixKey(uint64_t x) {
 // holds both strands' hashes of a window anyway (hf, hr), so one filter probe per read
 // position answers both strands -- half the L2 requests of probing each strand's hash.
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
-static const uint32_t kFilterMinBitsPerKey = 3;
+static const uint32_t kFilterMinBitsPerKey = 8;
 
 // reverse complement of a 2-bit packed h-mer (first base most significant)
 inline uint64_t revcompKeyHost(uint64_t key, uint32_t h) {
@@ -108,11 +109,37 @@ inline uint64_t filterMask(uint32_t B) {
 	return (uint64_t) lo | ((uint64_t) hi << 32);
 }
 
+// Uninitialised, owning array (the multi-GB table is first-touched by the build threads
+// instead of being value-initialised by one)
+template <typename T>
+struct RawArray {
+	T *p = NULL;
+	size_t n = 0;
+	RawArray() {}
+	RawArray(const RawArray &) = delete;
+	RawArray &operator=(const RawArray &) = delete;
+	~RawArray() { free(p); }
+	bool alloc(size_t count) {
+		free(p);
+		n = 0;
+		p = (T *) malloc(sizeof(T) * (count ? count : 1));
+		if (p == NULL)
+			return false;
+		n = count;
+		return true;
+	}
+	size_t size() const { return n; }
+	T *data() { return p; }
+	const T *data() const { return p; }
+	T &operator[](size_t i) { return p[i]; }
+	const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct FlatIndex {
 	uint32_t hash_len = 0;
 	uint64_t n_table_buckets = 0; // power of two
 	uint64_t n_keys = 0;
-	std::vector<TableSlot> table; // n_table_buckets * kSlotsPerBucket
+	RawArray<TableSlot> table;    // n_table_buckets * kSlotsPerBucket
 	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
 	uint32_t filter_shift = 0;    // 32 - log2(filter words)
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table

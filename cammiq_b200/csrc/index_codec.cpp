@@ -66,6 +66,33 @@ struct ByteCursor {
 	const uint8_t *p;
 	uint64_t n, pos;
 	bool overrun;
+	// fast paths for the common widths (unaligned load + byte swap), with the same overrun rule
+	inline uint64_t be8() {
+		if (pos + 8 <= n) {
+			uint64_t v;
+			memcpy(&v, p + pos, 8);
+			pos += 8;
+			return __builtin_bswap64(v);
+		}
+		return be(8);
+	}
+	inline uint32_t be4() {
+		if (pos + 4 <= n) {
+			uint32_t v;
+			memcpy(&v, p + pos, 4);
+			pos += 4;
+			return __builtin_bswap32(v);
+		}
+		return (uint32_t) be(4);
+	}
+	inline uint16_t be2() {
+		if (pos + 2 <= n) {
+			uint16_t v = (uint16_t) ((p[pos] << 8) | p[pos + 1]);
+			pos += 2;
+			return v;
+		}
+		return (uint16_t) be(2);
+	}
 	inline uint64_t be(int nbytes) {
 		uint64_t v = 0;
 		for (int i = 0; i < nbytes; i++) {
@@ -131,14 +158,14 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 
 	auto readLeaf = [&](uint8_t depth) -> uint32_t {
 		uint32_t id = (uint32_t) out.ref_id1.size();
-		uint32_t r1 = (uint32_t) ic.be(4), r2 = 0;
+		uint32_t r1 = ic.be4(), r2 = 0;
 		uint16_t c1, c2 = 0;
 		if (dd) {
-			r2 = (uint32_t) ic.be(4);
-			c1 = (uint16_t) ic.be(2);
-			c2 = (uint16_t) ic.be(2);
+			r2 = ic.be4();
+			c1 = ic.be2();
+			c2 = ic.be2();
 		} else
-			c1 = (uint16_t) ic.be(2);
+			c1 = ic.be2();
 		out.ref_id1.push_back(r1);
 		out.ref_id2.push_back(r2);
 		out.ucount1.push_back(c1);
@@ -150,7 +177,7 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 	};
 
 	std::vector<Frame> stack;
-	uint64_t key = ic.be(8);
+	uint64_t key = ic.be8();
 	while (key != UINT64_MAX) {
 		if (ic.overrun) {
 			err = "Index " + path + ": INT stream ends before the END64 terminator.";
@@ -214,7 +241,7 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 		}
 		out.bucket_key.push_back(key);
 		out.bucket_root.push_back(root);
-		key = ic.be(8);
+		key = ic.be8();
 		if (out.ref_id1.size() >= 0x7FFFFFF0ull || out.nodes.size() / 4 >= 0x7FFFFFF0ull) {
 			err = "Index " + path + ": more than 2^31 leaves or nodes.";
 			return CQ_EFORMAT;

@@ -19,6 +19,12 @@ CLI = os.path.join(REPO, "cammiq_b200", "cammiq")
 KEEP = re.compile(r"^(Querying|Number of unlabeled|Number of reads with conflict|Completed query|Hash Length)")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def built_cli():
+    if not os.access(CLI, os.X_OK):
+        subprocess.check_call(["make", "-C", os.path.join(REPO, "cammiq_b200", "csrc"), "../cammiq"])
+
+
 def run_cli(args, exe=CLI):
     res = subprocess.run([exe] + args, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:]
