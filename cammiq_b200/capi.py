@@ -18,7 +18,7 @@ import numpy as np
 MODE_P, MODE_SC = 0, 1
 TABLE_U, TABLE_D = 0, 1
 CLASS_UNLABELED, CLASS_CONFLICT, CLASS_U, CLASS_D_PAIR, CLASS_UD, CLASS_D_INTER = range(6)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -80,7 +80,9 @@ class Timing(C.Structure):
                 ("bucket_hits", C.c_uint64), ("leaf_hits", C.c_uint64), ("chained_loads", C.c_uint64),
                 ("pack_ms_sum", C.c_double), ("scan_ms_sum", C.c_double), ("reduce_ms_sum", C.c_double),
                 ("steps", C.c_uint64), ("grid_blocks", C.c_uint32), ("blocks_per_sm", C.c_uint32),
-                ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32)]
+                ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32),
+                ("host_pack_ms", C.c_double), ("host_pack_threads", C.c_uint32), ("reserved0", C.c_uint32),
+                ("h2d_bytes", C.c_uint64)]
 
 
 # every symbol include/cammiq_gpu.h declares: (restype, argtypes)
@@ -101,6 +103,12 @@ SYMBOLS = {
     "cq_index_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "cq_query": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                            C.c_uint64, C.POINTER(Result)]),
+    "cq_ctx_set_host_packing": (C.c_int, [C.c_void_p, C.c_int]),
+    "cq_pack_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
+                                C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "cq_pack_isa": (C.c_char_p, []),
+    "cq_query_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                  C.c_uint64, C.POINTER(Result)]),
     "cq_reset": (C.c_int, [C.c_void_p]),
     "cq_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cq_host_free": (None, [C.c_void_p]),
@@ -305,6 +313,27 @@ class Context:
                               lengths.ctypes.data, n, C.byref(res)))
         return self._finish(mode, res, keep, n)
 
+    def set_host_packing(self, threads):
+        """threads > 0: cq_query packs reads to 2 bits per base on the host before the copy;
+        0: ASCII crosses PCIe; < 0: library default."""
+        _check(lib().cq_ctx_set_host_packing(self._h, threads))
+        return self
+
+    def query_packed(self, mode, packed, offsets, lengths, stride=0, per_read=False, leaf_cap=0,
+                     want_rcount=True, pairs_cap=1 << 16, buffers=None):
+        """Reads already packed by pack_reads(): packed uint8[], offsets uint64[] or None (fixed
+        stride in bytes), lengths uint8[] (0 = invalid read)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(lengths)
+        res, keep = self._result(mode, n, per_read, leaf_cap, want_rcount, pairs_cap, buffers)
+        _check(lib().cq_query_packed(self._h, mode, packed.ctypes.data,
+                                     offsets.ctypes.data if offsets is not None else None, stride,
+                                     lengths.ctypes.data, n, C.byref(res)))
+        return self._finish(mode, res, keep, n)
+
     # device-resident plumbing -------------------------------------------------------------
     def stage(self, bases, offsets, lengths, stride=0):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
@@ -379,3 +408,27 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def pack_isa():
+    return lib().cq_pack_isa().decode()
+
+
+def pack_reads(bases, offsets, lengths, stride=0, threads=1, packed_stride=None):
+    """Host-only: ASCII reads -> (packed uint8[n, packed_stride], lengths uint8[n] with 0 for
+    invalid reads, n_invalid).  Layout: include/cammiq_gpu.h (cq_pack_reads)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(lengths)
+    if packed_stride is None:
+        packed_stride = (int(lengths.max()) + 3) // 4 if n else 1
+    packed = np.zeros((max(n, 1), max(packed_stride, 1)), dtype=np.uint8)
+    out_len = np.zeros(max(n, 1), dtype=np.uint8)
+    bad = C.c_uint64()
+    _check(lib().cq_pack_reads(bases.ctypes.data, offsets.ctypes.data if offsets is not None else None, stride,
+                               lengths.ctypes.data, n, threads, packed.ctypes.data, packed_stride,
+                               out_len.ctypes.data, C.byref(bad)))
+    return packed[:n], out_len[:n], bad.value
+

@@ -19,6 +19,7 @@
 #include "../../include/cammiq_gpu.h"
 #include "flat_index.hpp"
 #include "index_codec.hpp"
+#include "pack_reads.hpp"
 #include "scan_kernels.cuh"
 
 using namespace cammiq;
@@ -78,15 +79,26 @@ struct cq_ctx {
 	bool staged_has_offsets = false;
 	uint32_t staged_max_len = 0;
 	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
-	size_t last_dyn_smem[4] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
-	int last_per_sm[4] = {0, 0, 0, 0};
-	// double-buffered host->device pipeline of cq_query
+	size_t last_dyn_smem[8] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1,
+		(size_t) -1}; // per kernel variant
+	int last_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	// host->device pipeline of cq_query: kStages chunk buffers rotate through copy and scan
+	static const int kStages = 3;
 	cudaStream_t copy_stream = NULL;
-	cudaEvent_t ev_copied[2] = {NULL, NULL}, ev_free[2] = {NULL, NULL};
-	uint8_t *d_cbases[2] = {NULL, NULL};
-	uint64_t *d_coffsets[2] = {NULL, NULL};
-	uint8_t *d_clengths[2] = {NULL, NULL};
-	size_t cap_cbases[2] = {0, 0}, cap_coffsets[2] = {0, 0}, cap_clengths[2] = {0, 0};
+	cudaEvent_t ev_copied[kStages] = {NULL, NULL, NULL}, ev_free[kStages] = {NULL, NULL, NULL};
+	uint8_t *d_cbases[kStages] = {NULL, NULL, NULL};
+	uint64_t *d_coffsets[kStages] = {NULL, NULL, NULL};
+	uint32_t *d_coffsets32[kStages] = {NULL, NULL, NULL};
+	uint8_t *d_clengths[kStages] = {NULL, NULL, NULL};
+	size_t cap_cbases[kStages] = {0, 0, 0}, cap_coffsets[kStages] = {0, 0, 0}, cap_coffsets32[kStages] = {0, 0, 0},
+		cap_clengths[kStages] = {0, 0, 0};
+	// host packing (cq_ctx_set_host_packing): worker pool + pinned staging of the packed chunks
+	int pack_threads = 0;
+	WorkerPool *pool = NULL;
+	uint8_t *h_pbases[kStages] = {NULL, NULL, NULL};
+	uint8_t *h_plengths[kStages] = {NULL, NULL, NULL};
+	uint32_t *h_poffsets[kStages] = {NULL, NULL, NULL};
+	size_t cap_h_pbases[kStages] = {0, 0, 0}, cap_h_plengths[kStages] = {0, 0, 0}, cap_h_poffsets[kStages] = {0, 0, 0};
 	// SC pair records (device, grows)
 	unsigned long long *d_pairs = NULL;
 	size_t cap_pairs = 0;
@@ -245,6 +257,15 @@ static void freeDevice(cq_ctx *c) {
 	c->has_index = false;
 }
 
+// CAMMIQ_PACK_THREADS if set, else min(16, hardware threads) on hosts with at least 4, else 0
+static int defaultPackThreads() {
+	const char *env = getenv("CAMMIQ_PACK_THREADS");
+	if (env != NULL)
+		return std::max(0, atoi(env));
+	const unsigned hw = std::thread::hardware_concurrency();
+	return hw >= 4 ? (int) std::min(hw, 16u) : 0;
+}
+
 extern "C" int cq_ctx_create(int device, void *stream, cq_ctx **out) {
 	if (out == NULL)
 		return fail(CQ_EINVAL, "cq_ctx_create: NULL argument.");
@@ -277,12 +298,14 @@ extern "C" int cq_ctx_create(int device, void *stream, cq_ctx **out) {
 		}
 		c->own_stream = true;
 	}
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < 2; i++)
 		cudaEventCreate(&c->ev[i]);
+	for (int i = 0; i < cq_ctx::kStages; i++) {
 		cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming);
 	}
 	cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+	c->pack_threads = defaultPackThreads();
 	*out = c;
 	return CQ_OK;
 }
@@ -297,12 +320,15 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
 	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
 	cudaFree(c->d_leaf_d);
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < 2; i++)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < cq_ctx::kStages; i++) {
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 		if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
-		cudaFree(c->d_cbases[i]); cudaFree(c->d_coffsets[i]); cudaFree(c->d_clengths[i]);
+		cudaFree(c->d_cbases[i]); cudaFree(c->d_coffsets[i]); cudaFree(c->d_coffsets32[i]); cudaFree(c->d_clengths[i]);
+		cudaFreeHost(c->h_pbases[i]); cudaFreeHost(c->h_plengths[i]); cudaFreeHost(c->h_poffsets[i]);
 	}
+	delete c->pool;
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	for (auto &se : c->steps)
 		for (int i = 0; i < 4; i++)
@@ -469,6 +495,8 @@ struct ReadBatch {
 	const uint8_t *lengths;
 	uint64_t n, first;
 	uint32_t max_len;
+	bool packed;               // 2-bit codes (ScanParams) instead of ASCII
+	const uint32_t *offsets32; // packed batches: batch-relative 32-bit offsets
 };
 
 static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
@@ -489,13 +517,15 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.filter_shift = c->filter_shift;
 	sp.bases = rb.bases;
 	sp.offsets = rb.offsets;
+	sp.offsets32 = rb.offsets32;
 	sp.stride = rb.stride;
 	sp.read_base = rb.first;
 	sp.lengths = rb.lengths;
 	sp.n_reads = rb.n;
 	// staging buffer: the byte range 32 back-to-back reads of the longest length span
 	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
-	const uint32_t tile_cap = (32 * std::max<uint32_t>(rb.max_len, 1) + 32 + 127) & ~127u;
+	const uint32_t read_bytes = rb.packed ? (std::max<uint32_t>(rb.max_len, 1) + 3) / 4 : std::max<uint32_t>(rb.max_len, 1);
+	const uint32_t tile_cap = (32 * read_bytes + (rb.packed ? 64 : 32) + 127) & ~127u;
 	sp.tile_cap = tile_cap;
 	{
 		const char *dbg = getenv("CAMMIQ_DEBUG_FLAGS");
@@ -523,10 +553,13 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 		sp.read_leaf_d = c->d_leaf_d + rb.first * c->leaf_cap;
 	}
 	const bool filt = c->d_filter != NULL;
-	const void *kern = mode == CQ_MODE_P
-		? (filt ? (const void *) scan_reads_kernel<CQ_MODE_P, true> : (const void *) scan_reads_kernel<CQ_MODE_P, false>)
-		: (filt ? (const void *) scan_reads_kernel<CQ_MODE_SC, true> : (const void *) scan_reads_kernel<CQ_MODE_SC, false>);
-	const int variant = mode * 2 + (filt ? 1 : 0);
+	static const void *const kernels[8] = {
+		(const void *) scan_reads_kernel<CQ_MODE_P, false, false>, (const void *) scan_reads_kernel<CQ_MODE_P, false, true>,
+		(const void *) scan_reads_kernel<CQ_MODE_P, true, false>, (const void *) scan_reads_kernel<CQ_MODE_P, true, true>,
+		(const void *) scan_reads_kernel<CQ_MODE_SC, false, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, false, true>,
+		(const void *) scan_reads_kernel<CQ_MODE_SC, true, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, true, true>};
+	const int variant = mode * 4 + (filt ? 2 : 0) + (rb.packed ? 1 : 0);
+	const void *kern = kernels[variant];
 	if (dyn_smem != c->last_dyn_smem[variant]) {
 		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
 		int per_sm = 0;
@@ -625,7 +658,7 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	ReadBatch rb = {c->d_bases - c->staged_shift, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
-		c->staged_reads, 0, c->staged_max_len};
+		c->staged_reads, 0, c->staged_max_len, false, NULL};
 	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
@@ -710,14 +743,131 @@ static int fetchPerRead(cq_ctx *c, uint64_t n, cq_result *out) {
 
 static const uint64_t kChunkReads = 1u << 20; // reads per pipeline stage of cq_query
 
-extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
-		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
+template <typename T>
+static int ensureHost(T **ptr, size_t *cap, size_t need) {
+	if (need <= *cap && *ptr != NULL)
+		return CQ_OK;
+	if (*ptr) cudaFreeHost(*ptr);
+	*ptr = NULL;
+	*cap = 0;
+	size_t n = std::max<size_t>(need + need / 4, 64);
+	CQ_CUDA(cudaHostAlloc((void **) ptr, n * sizeof(T), cudaHostAllocDefault));
+	*cap = n;
+	return CQ_OK;
+}
+
+// Chunks of reads flow host -> device on the copy stream while earlier chunks are scanned on
+// the compute stream.  `packed`: the caller's buffer already holds 2-bit reads.
+static int pipelineDirect(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	int rc;
+	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
+		const int b = (int) (k % cq_ctx::kStages);
+		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
+		uint64_t lo = ~0ull, hi = 0;
+		uint32_t max_len = 1;
+		if (offsets) {
+			for (uint64_t i = first; i < first + n; i++) {
+				lo = std::min(lo, offsets[i]);
+				hi = std::max(hi, offsets[i] + (packed ? packedBytes(lengths[i]) : lengths[i]));
+				max_len = std::max<uint32_t>(max_len, lengths[i]);
+			}
+		} else {
+			for (uint64_t i = first; i < first + n; i++)
+				max_len = std::max<uint32_t>(max_len, lengths[i]);
+			// fixed stride: only the reads within 255 bytes of the chunk's end can set its extent
+			lo = first * stride;
+			hi = lo;
+			for (uint64_t i = first + n; i-- > first;) {
+				hi = std::max(hi, i * stride + (packed ? packedBytes(lengths[i]) : lengths[i]));
+				if ((first + n - 1 - i) * stride >= 255)
+					break;
+			}
+		}
+		if (hi < lo) hi = lo;
+		const uint64_t copy_lo = lo & ~15ull, copy_bytes = hi - copy_lo;
+		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], copy_bytes + 64)) != 0) return rc;
+		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], n)) != 0) return rc;
+		if (offsets && (rc = ensure(&c->d_coffsets[b], &c->cap_coffsets[b], n)) != 0) return rc;
+		if (k >= (uint64_t) cq_ctx::kStages)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+		else if (k == 0)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0)); // after earlier work on the compute stream
+		if (copy_bytes > 0)
+			CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], bases + copy_lo, copy_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+		CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], lengths + first, n, cudaMemcpyHostToDevice, c->copy_stream));
+		if (offsets)
+			CQ_CUDA(cudaMemcpyAsync(c->d_coffsets[b], offsets + first, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+		c->timing.h2d_bytes += copy_bytes + n + (offsets ? n * 8 : 0);
+		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+		ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len,
+			packed, NULL};
+		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
+		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
+	}
+	return CQ_OK;
+}
+
+// ASCII reads are packed to 2 bits per base by the worker pool, chunk by chunk, into pinned
+// staging; chunk k is packed while chunk k-1 crosses PCIe and chunk k-2 is scanned.
+static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	int rc;
+	if (c->pool == NULL || c->pool->size() != c->pack_threads) {
+		delete c->pool;
+		c->pool = new WorkerPool(c->pack_threads);
+	}
+	const AsciiReads in = {bases, offsets, stride, lengths};
+	const bool dense = offsets != NULL;
+	double pack_ms = 0;
+	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
+		const int b = (int) (k % cq_ctx::kStages);
+		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
+		// the pinned staging of this slot is free once its previous copy has left the host
+		if (k >= (uint64_t) cq_ctx::kStages)
+			CQ_CUDA(cudaEventSynchronize(c->ev_copied[b]));
+		auto p0 = std::chrono::high_resolution_clock::now();
+		const PackedLayout layout = planBatch(*c->pool, lengths, first, n, dense);
+		if ((rc = ensureHost(&c->h_pbases[b], &c->cap_h_pbases[b], (size_t) layout.total_bytes + 64)) != 0) return rc;
+		if ((rc = ensureHost(&c->h_plengths[b], &c->cap_h_plengths[b], (size_t) n)) != 0) return rc;
+		if (dense && (rc = ensureHost(&c->h_poffsets[b], &c->cap_h_poffsets[b], (size_t) n)) != 0) return rc;
+		packBatch(*c->pool, in, first, n, layout, c->h_pbases[b], c->h_poffsets[b], c->h_plengths[b]);
+		pack_ms += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - p0).count();
+		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], (size_t) layout.total_bytes + 64)) != 0) return rc;
+		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], (size_t) n)) != 0) return rc;
+		if (dense && (rc = ensure(&c->d_coffsets32[b], &c->cap_coffsets32[b], (size_t) n)) != 0) return rc;
+		if (k >= (uint64_t) cq_ctx::kStages)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+		else if (k == 0)
+			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0));
+		if (layout.total_bytes > 0)
+			CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], c->h_pbases[b], layout.total_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+		CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], c->h_plengths[b], n, cudaMemcpyHostToDevice, c->copy_stream));
+		if (dense)
+			CQ_CUDA(cudaMemcpyAsync(c->d_coffsets32[b], c->h_poffsets[b], n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+		c->timing.h2d_bytes += layout.total_bytes + n + (dense ? n * 4 : 0);
+		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+		// fixed stride: the kernel addresses read r at (first + r) * stride
+		ReadBatch rb = {dense ? c->d_cbases[b] : c->d_cbases[b] - first * layout.stride, NULL, layout.stride, c->d_clengths[b], n,
+			first, std::max<uint32_t>(layout.max_len, 1), true, dense ? c->d_coffsets32[b] : NULL};
+		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
+		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
+	}
+	c->timing.host_pack_ms = pack_ms;
+	c->timing.host_pack_threads = (uint32_t) c->pack_threads;
+	return CQ_OK;
+}
+
+static int queryHost(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out, const char *who) {
 	if (c == NULL || !c->has_index)
-		return fail(CQ_ESTATE, "cq_query: no index resident (call cq_index_upload first).");
+		return fail(CQ_ESTATE, std::string(who) + ": no index resident (call cq_index_upload first).");
 	if (out == NULL || (mode != CQ_MODE_P && mode != CQ_MODE_SC))
-		return fail(CQ_EINVAL, "cq_query: NULL result or bad mode.");
+		return fail(CQ_EINVAL, std::string(who) + ": NULL result or bad mode.");
 	if (n_reads > 0 && (bases == NULL || lengths == NULL))
-		return fail(CQ_EINVAL, "cq_query: NULL read buffers.");
+		return fail(CQ_EINVAL, std::string(who) + ": NULL read buffers.");
 	CQ_CUDA(cudaSetDevice(c->device));
 	auto t0 = std::chrono::high_resolution_clock::now();
 	c->want_per_read = out->read_class != NULL && out->read_rid_a != NULL && out->read_rid_b != NULL;
@@ -730,51 +880,14 @@ extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	CQ_CUDA(cudaEventRecord(c->ev[0], c->stream));
-	// Chunks of reads flow host -> device on the copy stream while the previous chunk is
-	// scanned on the compute stream (two staging buffers).
-	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
-		const int b = (int) (k & 1);
-		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
-		uint64_t lo = ~0ull, hi = 0;
-		uint32_t max_len = 1;
-		if (offsets) {
-			for (uint64_t i = first; i < first + n; i++) {
-				lo = std::min(lo, offsets[i]);
-				hi = std::max(hi, offsets[i] + lengths[i]);
-				max_len = std::max<uint32_t>(max_len, lengths[i]);
-			}
-		} else {
-			for (uint64_t i = first; i < first + n; i++)
-				max_len = std::max<uint32_t>(max_len, lengths[i]);
-			// fixed stride: only the reads within 255 bytes of the chunk's end can set its extent
-			lo = first * stride;
-			hi = lo;
-			for (uint64_t i = first + n; i-- > first;) {
-				hi = std::max(hi, i * stride + lengths[i]);
-				if ((first + n - 1 - i) * stride >= 255)
-					break;
-			}
-		}
-		if (hi < lo) hi = lo;
-		const uint64_t copy_lo = lo & ~15ull, copy_bytes = hi - copy_lo;
-		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], copy_bytes + 32)) != 0) return rc;
-		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], n)) != 0) return rc;
-		if (offsets && (rc = ensure(&c->d_coffsets[b], &c->cap_coffsets[b], n)) != 0) return rc;
-		if (k >= 2)
-			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
-		else if (k == 0)
-			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0)); // after earlier work on the compute stream
-		if (copy_bytes > 0)
-			CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], bases + copy_lo, copy_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-		CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], lengths + first, n, cudaMemcpyHostToDevice, c->copy_stream));
-		if (offsets)
-			CQ_CUDA(cudaMemcpyAsync(c->d_coffsets[b], offsets + first, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
-		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-		ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len};
-		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
-		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
-	}
+	c->timing.h2d_bytes = 0;
+	c->timing.host_pack_ms = 0;
+	c->timing.host_pack_threads = 0;
+	if (!packed && c->pack_threads > 0)
+		rc = pipelineHostPack(c, mode, bases, offsets, stride, lengths, n_reads);
+	else
+		rc = pipelineDirect(c, mode, packed, bases, offsets, stride, lengths, n_reads);
+	if (rc != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
 	CQ_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -789,6 +902,40 @@ extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_
 	c->timing.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
 	return rc;
 }
+
+extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
+	return queryHost(c, mode, false, bases, offsets, stride, lengths, n_reads, out, "cq_query");
+}
+
+extern "C" int cq_query_packed(cq_ctx *c, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
+	return queryHost(c, mode, true, packed, offsets, stride, lengths, n_reads, out, "cq_query_packed");
+}
+
+extern "C" int cq_ctx_set_host_packing(cq_ctx *c, int threads) {
+	if (c == NULL)
+		return fail(CQ_EINVAL, "cq_ctx_set_host_packing: NULL context.");
+	c->pack_threads = threads < 0 ? defaultPackThreads() : std::min(threads, 256);
+	return CQ_OK;
+}
+
+extern "C" int cq_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint64_t stride, const uint8_t *lengths,
+		uint64_t n_reads, int threads, uint8_t *packed, uint64_t packed_stride, uint8_t *packed_lengths, uint64_t *n_invalid) {
+	if (n_reads > 0 && (bases == NULL || lengths == NULL || packed == NULL || packed_lengths == NULL))
+		return fail(CQ_EINVAL, "cq_pack_reads: NULL buffers.");
+	WorkerPool pool(std::max(1, std::min(threads, 256)));
+	const AsciiReads in = {bases, offsets, stride, lengths};
+	PackedLayout layout = planBatch(pool, lengths, 0, n_reads, false);
+	if (packed_stride < layout.stride)
+		return fail(CQ_EINVAL, "cq_pack_reads: packed_stride is smaller than ceil(longest read / 4).");
+	layout.stride = packed_stride;
+	const uint64_t bad = packBatch(pool, in, 0, n_reads, layout, packed, NULL, packed_lengths);
+	if (n_invalid) *n_invalid = bad;
+	return CQ_OK;
+}
+
+extern "C" const char *cq_pack_isa(void) { return packIsaName(); }
 
 extern "C" int cq_host_alloc(size_t bytes, void **out) {
 	if (out == NULL)

@@ -49,9 +49,13 @@ struct ScanParams {
 	const uint2 *leaf_d_ref;
 	uint32_t h;
 	uint32_t n_genomes;
-	// reads: ASCII in device memory, exactly the state query64_* consumes
+	// reads in device memory.  ASCII (exactly the state query64_* consumes), or PACKED: 2 bits per
+	// base, base j of a read in byte j/4 at bits 7-2*(j%4)..6-2*(j%4) (first base most
+	// significant), ceil(len/4) bytes per read, validated on the host (an invalid read arrives
+	// with length 0)
 	const uint8_t *bases;
 	const uint64_t *offsets;  // NULL: read i starts at (read_base + i)*stride
+	const uint32_t *offsets32; // PACKED only: 32-bit offsets (batch-relative), or NULL
 	uint64_t stride;
 	uint64_t read_base;       // caller's index of this launch's first read (chunked submission)
 	const uint8_t *lengths;
@@ -167,19 +171,27 @@ __device__ __forceinline__ const uint8_t *slotBases(const ScanParams &p, const W
 }
 
 // base `j` of strand `strand` of a read (strand 1 = reverse complement, query.cpp:447-450)
+template <bool PACKED>
 __device__ __forceinline__ uint32_t strandBase(const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t j) {
-	bool bad = false;
-	uint32_t c = strand ? 3u - decodeBase(s[rl - 1 - j], bad) : decodeBase(s[j], bad);
-	return c;
+	const uint32_t at = strand ? rl - 1 - j : j;
+	uint32_t c;
+	if (PACKED) {
+		c = ((uint32_t) s[at >> 2] >> (6u - 2u * (at & 3u))) & 3u;
+	} else {
+		bool bad = false;
+		c = decodeBase(s[at], bad);
+	}
+	return strand ? 3u - c : c;
 }
 
 // Walk the CSR trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).
+template <bool PACKED>
 __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes,
 		const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t next) {
 	while (ref != kRefNone && !(ref & kRefLeafTag)) {
 		if (next >= rl)
 			return kRefNone;
-		uint32_t code = strandBase(s, rl, strand, next);
+		uint32_t code = strandBase<PACKED>(s, rl, strand, next);
 		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
 		next++;
 	}
@@ -202,11 +214,26 @@ __device__ __forceinline__ unsigned long long reverseGroups(unsigned long long x
 // significant, right-aligned).  The reverse-complement strand's window is the reverse
 // complement of the forward window [rl-j-n, rl-j); staged reads are decoded four bases per
 // 32-bit shared load (the bytes were validated by phase 1).
+template <bool PACKED>
 __device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, bool in_smem, uint32_t rl, uint32_t strand,
 		uint32_t j, uint32_t n) {
 	const uint32_t i = strand ? rl - j - n : j;
 	unsigned long long hv = 0;
-	if (in_smem) {
+	if (PACKED) {
+		// the window is bits [2i, 2i+2n) of the read's big-endian bit stream
+		if (in_smem) {
+			// three aligned words cover the <= 9 bytes the window touches (the staging buffer has slack)
+			const uint32_t a = smemAddr(s) + (i >> 2);
+			const uint32_t w0 = __byte_perm(ldsWord(a & ~3u), 0u, 0x0123), w1 = __byte_perm(ldsWord((a & ~3u) + 4u), 0u, 0x0123),
+				w2 = __byte_perm(ldsWord((a & ~3u) + 8u), 0u, 0x0123);
+			const uint32_t sh = (a & 3u) * 8u + 2u * (i & 3u); // 0..30
+			const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+			hv = (((unsigned long long) hi << 32) | lo) >> (64 - 2 * n);
+		} else {
+			for (uint32_t t = 0; t < n; t++)
+				hv = (hv << 2) | (((uint32_t) s[(i + t) >> 2] >> (6u - 2u * ((i + t) & 3u))) & 3u);
+		}
+	} else if (in_smem) {
 		const uint32_t a0 = smemAddr(s) + i;
 		for (uint32_t t = 0; t < n; t += 4) {
 			const uint32_t a = a0 + t;
@@ -227,6 +254,7 @@ __device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, boo
 
 // Phase 2: the warp drains its candidate queue.  One candidate per lane: recompute the h-mer,
 // probe the prefix table (HBM), descend, append leaves to the owning read's hit list.
+template <bool PACKED>
 __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, const uint8_t *buf, uint32_t *warp_spill,
 		int lane, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
@@ -239,7 +267,7 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 			const uint32_t slot = item >> 9, strand = (item >> 8) & 1u, pos = item & 0xFFu;
 			const uint8_t *s = slotBases(p, ws, buf, slot);
 			const uint32_t rl = ws.rl[slot];
-			const unsigned long long hv = strandWindow(s, ws.staged != 0, rl, strand, pos, h);
+			const unsigned long long hv = strandWindow<PACKED>(s, ws.staged != 0, rl, strand, pos, h);
 			uint64_t b = mixKey(hv) & p.table_mask;
 			unsigned long long k0, r0, k1, r1, refs = 0;
 			bool found = false;
@@ -254,8 +282,8 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 			}
 			if (found) {
 				uint32_t leaf[2];
-				leaf[0] = descend((uint32_t) refs, p.nodes_u, s, rl, strand, pos + h);
-				leaf[1] = descend((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, pos + h);
+				leaf[0] = descend<PACKED>((uint32_t) refs, p.nodes_u, s, rl, strand, pos + h);
+				leaf[1] = descend<PACKED>((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, pos + h);
 #pragma unroll
 				for (int t = 0; t < 2; t++) {
 					if (leaf[t] == kRefNone)
@@ -278,13 +306,19 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 	__syncwarp();
 }
 
+__device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
 __device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
 	uint32_t v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
 
-template <int MODE, bool FILTER>
+template <int MODE, bool FILTER, bool PACKED>
 __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams p) {
 	// [8 warps][tile_cap bytes of ASCII] | [2*(G+1) u32 genome counters]
 	extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -333,9 +367,12 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 		SubTile t;
 		const uint64_t r = sub_idx * 32 + lane;
 		t.have = r < p.n_reads;
-		t.off = t.have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
+		if (PACKED)
+			t.off = t.have ? (p.offsets32 ? (unsigned long long) p.offsets32[r] : p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
+		else
+			t.off = t.have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
 		t.rl = t.have ? p.lengths[r] : 0;
-		unsigned long long lo = t.off, hi = t.have ? t.off + t.rl : 0ull;
+		unsigned long long lo = t.off, hi = t.have ? t.off + (PACKED ? (t.rl + 3u) >> 2 : t.rl) : 0ull;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			unsigned long long tl = __shfl_xor_sync(0xffffffffu, lo, o), th = __shfl_xor_sync(0xffffffffu, hi, o);
@@ -393,7 +430,11 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 		for (uint32_t j0 = 0; j0 < wmax; j0 += kStepUnroll) {
 			// bytes j0..j0+3 of the read (garbage past rl is masked below)
 			uint32_t w4 = 0;
-			if (j0 < rl) {
+			if (PACKED) {
+				// one byte = the four codes of this iteration (validated and zero-padded by the host)
+				if (j0 < rl)
+					w4 = staged ? ldsU8(sbase + (j0 >> 2)) : (uint32_t) gbase[j0 >> 2];
+			} else if (j0 < rl) {
 				if (staged) {
 					const uint32_t a = sbase + j0;
 					w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
@@ -405,13 +446,18 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 			}
 			// codes: A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
 			// letter the code stands for (one byte permute)
-			const uint32_t t4 = (w4 >> 1) & 0x03030303u;
-			const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-			const uint32_t nib = code4 | (code4 >> 4);
-			const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-			const uint32_t left = rl > j0 ? rl - j0 : 0u;
-			const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
-			bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
+			uint32_t code4;
+			if (PACKED) {
+				code4 = w4;
+			} else {
+				const uint32_t t4 = (w4 >> 1) & 0x03030303u;
+				code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+				const uint32_t nib = code4 | (code4 >> 4);
+				const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+				const uint32_t left = rl > j0 ? rl - j0 : 0u;
+				const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
+				bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
+			}
 
 			uint2 ff[kStepUnroll];                                // FILTER: filter words
 			uint32_t bsel[kStepUnroll];
@@ -420,7 +466,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 #pragma unroll
 			for (int u = 0; u < kStepUnroll; u++) {
 				const uint32_t j = j0 + u;
-				const uint32_t c = (code4 >> (8 * u)) & 3u;
+				const uint32_t c = PACKED ? (code4 >> (6 - 2 * u)) & 3u : (code4 >> (8 * u)) & 3u;
 				hf = ((hf << 2) | c) & kmask;
 				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
 				if (j + 1 >= h && j < rl) {
@@ -484,11 +530,11 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 				__syncwarp();
 				// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
 				if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
-					drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+					drainQueue<PACKED>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 			}
 		}
 		const bool bad = bad4 != 0;
-		drainQueue(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+		drainQueue<PACKED>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 
 		// ---- phase 3: thread per read: leaf set -> decision (query.cpp:529-636) ------------------
 		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CQ_ABI_VERSION 1
+#define CQ_ABI_VERSION 2
 
 enum {
 	CQ_OK = 0,
@@ -191,6 +191,43 @@ typedef struct {
 int cq_query(cq_ctx *ctx, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads, cq_result *out);
 
+/* ------------------------------------------- 2-bit packed reads -- */
+/*
+ * The reference keeps reads as ASCII (`std::vector<uint8_t*> reads`, query.cpp:371-425) and so
+ * does cq_query's interface; ASCII is 4x the bytes PCIe has to move.  With host packing on,
+ * cq_query converts each chunk of reads to 2-bit codes with `threads` host threads (AVX-512 /
+ * AVX2 / scalar), validates them there, and overlaps pack -> copy -> scan chunk by chunk.
+ * Results are identical either way.  threads = 0 turns packing off (ASCII crosses PCIe, the
+ * kernel decodes); threads < 0 restores the default: CAMMIQ_PACK_THREADS if set, else
+ * min(16, hardware threads) when the host has at least 4, else off.
+ */
+int cq_ctx_set_host_packing(cq_ctx *ctx, int threads);
+
+/*
+ * Packed layout: base j of a read sits in byte j/4 at bits 7-2*(j%4)..6-2*(j%4) (A=0 C=1 G=2
+ * T=3, hash alphabet of query.cpp:1860-1883; first base most significant), ceil(len/4) bytes
+ * per read, unused low bits of the last byte zero.
+ *
+ * cq_pack_reads: host-only helper for callers that ingest reads themselves (a FASTQ parser
+ * writing straight into pinned buffers).  Read i goes to packed + i*packed_stride
+ * (packed_stride >= ceil(max length/4)); packed_lengths[i] = lengths[i], or 0 when the read
+ * holds a byte outside ACGTacgt (cq_query's rule for such reads then applies);
+ * *n_invalid (may be NULL) receives how many did.  Works without a GPU.
+ */
+int cq_pack_reads(const uint8_t *bases, const uint64_t *offsets, uint64_t stride, const uint8_t *lengths,
+		uint64_t n_reads, int threads, uint8_t *packed, uint64_t packed_stride, uint8_t *packed_lengths,
+		uint64_t *n_invalid);
+/* "avx512", "avx2" or "scalar": the packer this host runs. */
+const char *cq_pack_isa(void);
+
+/*
+ * cq_query over reads the caller already holds PACKED in host memory: read i =
+ * ceil(lengths[i]/4) bytes at packed[offsets[i]] (offsets NULL: at i*stride, stride in
+ * bytes).  lengths as produced by cq_pack_reads (0 = invalid read).  Otherwise as cq_query.
+ */
+int cq_query_packed(cq_ctx *ctx, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out);
+
 /* Zero the accumulated counters (cnt_u/d, rcount, nundet, nconf, n_invalid, pairs). */
 int cq_reset(cq_ctx *ctx);
 
@@ -236,6 +273,10 @@ typedef struct {
 	uint64_t steps;
 	/* geometry of the last scan launch */
 	uint32_t grid_blocks, blocks_per_sm, dyn_smem_bytes, regs_per_thread;
+	/* host packing of the last cq_query: wall time spent in the packer, threads used (0 = off) */
+	double host_pack_ms;
+	uint32_t host_pack_threads, reserved0;
+	uint64_t h2d_bytes;   /* bytes the last cq_query / cq_query_packed copied host->device */
 } cq_timing;
 /* Synchronises the stream, folds the per-step CUDA events into the sums and returns them. */
 int cq_get_timing(cq_ctx *ctx, cq_timing *out);

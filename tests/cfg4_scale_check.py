@@ -1,0 +1,88 @@
+"""BASELINE configs[3] shape on one GPU: 5000 synthetic genomes (~15 Gbp), index too large for
+the L2 filter -> the table-probing variant of the scan.  Run by hand on a GPU box
+(`python tests/cfg4_scale_check.py [genomes] [reads]`, needs ~100 GB of host RAM for the oracle);
+not collected by pytest.  Checks the size-independent properties (strand symmetry, additivity,
+conservation) on all reads and per-read equality with the oracle on the first 20000 reads.
+Writes gpurun_out/cfg4_check.json."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import cammiq_b200 as cq  # noqa: E402
+from cammiq_b200 import synthlib as sl  # noqa: E402
+
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
+rl = 150
+d = "/tmp/cfg4_g%d" % G
+p = sl.params(seed=4, n_genomes=G, genome_len=3_000_000, cluster_size=4)
+out = {"genomes": G, "reads": n, "read_len": rl}
+t = time.time()
+if not os.path.exists(d + "/index_u.bin1"):
+    out["index_stats"] = sl.write_index(p, d)
+out["index_write_s"] = time.time() - t
+t = time.time()
+idx = cq.Index(d + "/index_u.bin1", d + "/index_d.bin2")
+out["index_load_s"] = time.time() - t
+i = idx.info
+out["index"] = {"leaves_u": i.n_leaves_u, "leaves_d": i.n_leaves_d, "keys": i.n_keys, "table_gb": i.n_table_buckets * 32 / 1e9,
+                "filter_mb": i.filter_bytes >> 20, "device_gb": i.device_bytes / 1e9, "decode_ms": i.decode_ms, "flatten_ms": i.flatten_ms}
+print(out, flush=True)
+t = time.time()
+ctx = cq.Context(0).upload(idx, G)
+out["upload_s"] = time.time() - t
+reads, src = sl.make_reads(p, 0, n, rl, 0.01, want_src=True)
+lengths = np.full(n, rl, dtype=np.uint8)
+a = ctx.query(cq.MODE_P, reads.reshape(-1), None, lengths, stride=rl, per_read=True)
+tm = ctx.timing()
+out["scan_ms"] = tm["scan_ms"]
+out["reads_per_s_kernel"] = n / (tm["scan_ms"] * 1e-3)
+out["probes_per_s"] = tm["probes"] / (tm["scan_ms"] * 1e-3)
+ctx.reset()
+lut = np.arange(256, dtype=np.uint8)
+for x, y in zip(b"ACGT", b"TGCA"):
+    lut[x] = y
+rc = np.ascontiguousarray(lut[reads[:, ::-1]])
+b = ctx.query(cq.MODE_P, rc.reshape(-1), None, lengths, stride=rl, per_read=True)
+ctx.reset()
+ok = all(np.array_equal(a[k], b[k]) for k in ("cnt_u", "cnt_d", "rcount_u", "rcount_d", "read_class", "read_rid_a", "read_rid_b"))
+out["strand_symmetry"] = bool(ok)
+half = n // 2 + 777
+ctx.query(cq.MODE_P, reads[:half].reshape(-1), None, lengths[:half], stride=rl)
+c = ctx.query(cq.MODE_P, reads[half:].reshape(-1), None, lengths[half:], stride=rl)
+out["additivity"] = bool(all(np.array_equal(a[k], c[k]) for k in ("cnt_u", "cnt_d", "rcount_u", "rcount_d")))
+cls, ra, rb = a["read_class"], a["read_rid_a"], a["read_rid_b"]
+out["conservation"] = bool(int((cls == 0).sum()) == a["nundet"] and int((cls == 1).sum()) == a["nconf"]
+                           and int(a["cnt_u"].sum()) == int(((cls == 2) | (cls == 4)).sum()))
+single = (cls == 2) | (cls == 4) | (cls == 5)
+pair = cls == 3
+hit = np.where(single, ra == src, np.where(pair, (ra == src) | (rb == src), True))
+out["assigned_reads_on_source_genome_frac"] = float(hit[single | pair].mean())
+out["class_histogram"] = {int(k): int(v) for k, v in zip(*np.unique(cls, return_counts=True))}
+json.dump(out, open("gpurun_out/cfg4_check.json", "w"), indent=1)
+# oracle on a sample (test infrastructure; loads both tries on the host)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import oracle_lib as ol  # noqa: E402
+t = time.time()
+ou, od = ol.OracleIndex(d + "/index_u.bin1"), ol.OracleIndex(d + "/index_d.bin2")
+out["oracle_load_s"] = time.time() - t
+m = min(n, 20000)
+offs = np.arange(m, dtype=np.uint64) * rl
+t = time.time()
+o = ol.oracle_query(ou, od, ol.MODE_P, G, reads[:m].reshape(-1), offs, lengths[:m], per_read=True)
+out["oracle_query_s"] = time.time() - t
+ctx.reset()
+g = ctx.query(cq.MODE_P, reads[:m].reshape(-1), None, lengths[:m], stride=rl, per_read=True)
+out["oracle_sample_reads"] = m
+out["oracle_parity"] = bool(all(np.array_equal(np.asarray(o[k]), np.asarray(g[k])) for k in
+                                ("cnt_u", "cnt_d", "read_class", "read_rid_a", "read_rid_b"))
+                            and o["nundet"] == g["nundet"] and o["nconf"] == g["nconf"])
+out["oracle_rcount_parity"] = bool(np.array_equal(o["rcount_u"], g["rcount_u"]) and np.array_equal(o["rcount_d"], g["rcount_d"]))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/cfg4_check.json", "w"), indent=1)
+print(json.dumps(out, indent=1))

@@ -14,9 +14,12 @@ from golden_util import golden_cases, load_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["ascii_over_pcie", "host_packed"])
+def ctx(request):
+    """Every test runs through both host->device paths of cq_query: ASCII reads decoded by the
+    kernel, and reads packed to 2 bits per base by host threads before the copy."""
     c = cq.Context(0)
+    c.set_host_packing(0 if request.param == "ascii_over_pcie" else 3)
     yield c
     c.close()
 
