@@ -113,6 +113,7 @@ SYMBOLS = {
     "cq_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "cq_host_free": (None, [C.c_void_p]),
     "cq_reads_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "cq_reads_stage_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "cq_query_staged": (C.c_int, [C.c_void_p, C.c_int]),
     "cq_sync": (C.c_int, [C.c_void_p]),
     "cq_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
@@ -343,6 +344,16 @@ class Context:
         _check(lib().cq_reads_stage(self._h, bases.ctypes.data,
                                     offsets.ctypes.data if offsets is not None else None, stride,
                                     lengths.ctypes.data, len(lengths)))
+        _check(lib().cq_sync(self._h))
+
+    def stage_packed(self, packed, offsets, lengths, stride=0):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().cq_reads_stage_packed(self._h, packed.ctypes.data,
+                                           offsets.ctypes.data if offsets is not None else None, stride,
+                                           lengths.ctypes.data, len(lengths)))
         _check(lib().cq_sync(self._h))
 
     def query_staged(self, mode):

@@ -79,6 +79,7 @@ struct cq_ctx {
 	bool staged_has_offsets = false;
 	uint32_t staged_max_len = 0;
 	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
+	bool staged_packed = false;
 	size_t last_dyn_smem[8] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1,
 		(size_t) -1}; // per kernel variant
 	int last_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -445,7 +446,7 @@ static int foldStepEvents(cq_ctx *c) {
 	return CQ_OK;
 }
 
-extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+static int stageReads(cq_ctx *c, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads) {
 	if (c == NULL || !c->has_index)
 		return fail(CQ_ESTATE, "cq_reads_stage: no index resident.");
@@ -458,13 +459,13 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	for (uint64_t i = 0; i < n_reads; i++) {
 		uint64_t off = offsets ? offsets[i] : i * stride;
 		lo = std::min(lo, off);
-		hi = std::max(hi, off + lengths[i]);
+		hi = std::max(hi, off + (packed ? packedBytes(lengths[i]) : lengths[i]));
 		max_len = std::max<uint32_t>(max_len, lengths[i]);
 	}
 	if (hi < lo) lo = hi = 0;
 	const uint64_t copy_lo = lo & ~15ull, total = hi - copy_lo;
 	int rc;
-	if ((rc = ensure(&c->d_bases, &c->cap_bases, total + 32)) != 0) return rc;
+	if ((rc = ensure(&c->d_bases, &c->cap_bases, total + 64)) != 0) return rc;
 	if ((rc = ensure(&c->d_lengths, &c->cap_reads_len, n_reads)) != 0) return rc;
 	if (offsets && (rc = ensure(&c->d_offsets, &c->cap_reads_off, n_reads)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(c->ev[0], c->stream));
@@ -482,7 +483,18 @@ extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *o
 	c->staged_has_offsets = offsets != NULL;
 	c->staged_bytes = total;
 	c->staged_max_len = max_len;
+	c->staged_packed = packed;
 	return CQ_OK;
+}
+
+extern "C" int cq_reads_stage(cq_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	return stageReads(c, false, bases, offsets, stride, lengths, n_reads);
+}
+
+extern "C" int cq_reads_stage_packed(cq_ctx *c, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	return stageReads(c, true, packed, offsets, stride, lengths, n_reads);
 }
 
 // One launch of the scan (+ partial-count reduction) over a batch of reads resident on the
@@ -658,7 +670,7 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	ReadBatch rb = {c->d_bases - c->staged_shift, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
-		c->staged_reads, 0, c->staged_max_len, false, NULL};
+		c->staged_reads, 0, c->staged_max_len, c->staged_packed, NULL};
 	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include "fastq_reader.hpp"
+#include "../pack_reads.hpp"
 #include "query_driver.hpp"
 
 static bool validFile(const char *fn) {
@@ -45,7 +47,29 @@ static void printUsage() {
 		exit(EXIT_FAILURE);                  \
 	}
 
+// --dump_reads <fastq> [min_len] (diagnostic, not in the reference): what readFastq hands the
+// scan, one line per read: "<length> <bases>", '!' for a read the kernel will treat as invalid.
+static int dumpReads(const char *path, size_t min_len) {
+	const char *seed = getenv("CAMMIQ_SEED");
+	srand(seed ? (unsigned) atoi(seed) : 1u);
+	cammiq::ReadSet rs;
+	if (!cammiq::readFastq(path, min_len, rs)) {
+		fprintf(stderr, "Cannot open %s.\n", path);
+		return 1;
+	}
+	std::vector<uint8_t> line(256);
+	for (size_t i = 0; i < rs.size(); i++) {
+		cammiq::unpackRead(rs.bases + rs.offsets[i], rs.lengths[i], line.data());
+		printf("%u %.*s\n", (unsigned) rs.lengths[i], (int) rs.lengths[i], (const char *) line.data());
+	}
+	fprintf(stderr, "%lu reads, total length %lu, %lu with N, %d threads, %.1f ms\n", (unsigned long) rs.size(),
+		(unsigned long) rs.total_length, (unsigned long) rs.n_with_n, rs.threads, rs.parse_ms);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc >= 3 && std::string(argv[1]) == "--dump_reads")
+		return dumpReads(argv[2], argc >= 4 ? (size_t) atoi(argv[3]) : 0);
 	if (argc == 2) {
 		std::string val(argv[1]);
 		if (val == "--help" || val == "--HELP") {

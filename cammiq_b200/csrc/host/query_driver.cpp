@@ -238,7 +238,7 @@ void FqReader::queryGpu(size_t file_idx, int mode) {
 	}
 	const int ng = (int) ctxs.size();
 	if (ng == 1) {
-		if (cq_query(ctxs[0], mode, rs.bases, rs.offsets.data(), 0, rs.lengths.data(), n, &res) != 0)
+		if (cq_query_packed(ctxs[0], mode, rs.bases, rs.offsets.data(), 0, rs.lengths.data(), n, &res) != 0)
 			die("GPU query failed");
 	} else {
 		// reads sharded over the GPUs (index replicated), counters combined afterwards
@@ -247,7 +247,7 @@ void FqReader::queryGpu(size_t file_idx, int mode) {
 		for (int d = 0; d < ng; d++)
 			pool.emplace_back([&, d]() {
 				uint64_t lo = n * d / ng, hi = n * (d + 1) / ng;
-				rcs[d] = cq_reads_stage(ctxs[d], rs.bases, rs.offsets.data() + lo, 0, rs.lengths.data() + lo, hi - lo);
+				rcs[d] = cq_reads_stage_packed(ctxs[d], rs.bases, rs.offsets.data() + lo, 0, rs.lengths.data() + lo, hi - lo);
 				if (rcs[d] == 0) rcs[d] = cq_query_staged(ctxs[d], mode);
 				if (rcs[d] == 0) rcs[d] = cq_sync(ctxs[d]);
 			});

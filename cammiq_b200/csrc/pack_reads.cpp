@@ -117,6 +117,18 @@ struct SliceArgs {
 };
 typedef uint64_t (*SliceFn)(const SliceArgs &);
 
+// A core streams ~10 GB/s on its own; fetching a few reads ahead keeps more lines in flight.
+#ifdef CAMMIQ_X86
+#define CAMMIQ_PREFETCH(p) _mm_prefetch(reinterpret_cast<const char *>(p), _MM_HINT_T0)
+#else
+#define CAMMIQ_PREFETCH(p) __builtin_prefetch(p)
+#endif
+static size_t prefetchAhead() {
+	const char *e = getenv("CAMMIQ_PACK_PREFETCH");
+	return e ? (size_t) atol(e) : 4096;
+}
+static const size_t kPrefetchAhead = prefetchAhead();
+
 // the loop is stamped out per ISA so that the packer inlines into it
 #define CAMMIQ_SLICE_LOOP(NAME, TARGET, PACK)                                                     \
 	TARGET uint64_t NAME(const SliceArgs &x) {                                                    \
@@ -126,6 +138,8 @@ typedef uint64_t (*SliceFn)(const SliceArgs &);
 			const uint32_t len = x.in->lengths[i];                                                \
 			const uint8_t *src = x.in->bases + (x.in->offsets ? x.in->offsets[i] : i * x.in->stride); \
 			uint8_t *dst = x.out + (x.dense ? at : k * x.stride);                                 \
+			CAMMIQ_PREFETCH(src + kPrefetchAhead);                                                \
+			CAMMIQ_PREFETCH(src + kPrefetchAhead + 64);                                           \
 			const bool ok = PACK(src, len, dst);                                                  \
 			x.out_lengths[k] = ok ? (uint8_t) len : 0;                                            \
 			bad += ok ? 0 : 1;                                                                    \

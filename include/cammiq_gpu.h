@@ -245,6 +245,9 @@ void cq_host_free(void *p);
  */
 int cq_reads_stage(cq_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads);
+/* The same for reads the caller holds packed (layout and arguments of cq_query_packed). */
+int cq_reads_stage_packed(cq_ctx *ctx, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads);
 int cq_query_staged(cq_ctx *ctx, int mode);
 int cq_sync(cq_ctx *ctx);
 /* Copy the accumulated totals to host buffers (same semantics as cq_query's out). */
