@@ -51,6 +51,8 @@ FqReader::FqReader(uint32_t hl_u, const std::string &idx_u, uint32_t hl_d, const
 }
 
 FqReader::~FqReader() {
+	if (ctx_thread.joinable())
+		ctx_thread.join();
 	for (auto c : ctxs)
 		cq_ctx_destroy(c);
 	if (index != NULL)
@@ -63,8 +65,19 @@ FqReader::~FqReader() {
 
 // FqReader::loadIdx_p (query.cpp:109-123): both index files are decoded on two host threads
 // inside cq_index_load and flattened into the device layout.
+void FqReader::startContexts() {
+	ctxs.assign((size_t) n_gpus, NULL);
+	ctx_rc.assign((size_t) n_gpus, 0);
+	ctx_thread = std::thread([this]() {
+		for (int d = 0; d < n_gpus; d++)
+			if ((ctx_rc[(size_t) d] = cq_ctx_create(d, NULL, &ctxs[(size_t) d])) != 0 && ctx_err.empty())
+				ctx_err = cq_last_error();
+	});
+}
+
 void FqReader::loadIdx_p() {
 	uint64_t start = nowMs();
+	startContexts(); // CUDA start-up overlaps the index decode
 	if (cq_index_load(IDXFILEU.c_str(), IDXFILED.c_str(), 0.0, &index) != 0) {
 		fprintf(stderr, "%s\n", cq_last_error());
 		abort();
@@ -119,14 +132,23 @@ void FqReader::loadSmap() {
 
 	// The index becomes resident here: the counters are sized by the number of genomes.
 	const uint32_t G = (uint32_t) genomes.size() - 1;
+	const uint64_t t_ctx = nowMs();
+	if (ctx_thread.joinable())
+		ctx_thread.join();
+	else
+		startContexts(), ctx_thread.join();
+	const uint64_t t_up = nowMs();
 	for (int d = 0; d < n_gpus; d++) {
-		cq_ctx *c = NULL;
-		if (cq_ctx_create(d, NULL, &c) != 0)
-			die("Cannot create the GPU context");
-		ctxs.push_back(c);
-		if (cq_index_upload(c, index, G) != 0)
+		if (ctx_rc[(size_t) d] != 0 || ctxs[(size_t) d] == NULL) {
+			fprintf(stderr, "Cannot create the GPU context: %s\n", ctx_err.c_str());
+			abort();
+		}
+		if (cq_index_upload(ctxs[(size_t) d], index, G) != 0)
 			die("Cannot place the index on the GPU");
 	}
+	if (getenv("CAMMIQ_VERBOSE"))
+		fprintf(stderr, "[cammiq] waited %lu ms for the GPU context(s), index upload %lu ms\n",
+			(unsigned long) (t_up - t_ctx), (unsigned long) (nowMs() - t_up));
 #ifdef CAMMIQ_WITH_NCCL
 	if (n_gpus > 1 && g_comms.empty()) {
 		// communicator set-up belongs to start-up (like the index load), not to "Time for query"
@@ -202,6 +224,9 @@ void FqReader::readAll(size_t min_l) {
 		ReadSet *rs = new ReadSet();
 		readFastq(qfilenames[i], min_l, *rs); // a missing file yields an empty read set, as in the reference
 		reads.push_back(rs);
+		if (getenv("CAMMIQ_VERBOSE"))
+			fprintf(stderr, "[cammiq] %s: %lu reads parsed and packed in %.1f ms on %d threads (%lu with N)\n",
+				qfilenames[i].c_str(), (unsigned long) rs->size(), rs->parse_ms, rs->threads, (unsigned long) rs->n_with_n);
 		fprintf(stderr, "Loaded query file %s.\n", qfilenames[i].c_str());
 	}
 }

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/cammiq_gpu.h"
@@ -64,6 +65,11 @@ private:
 
 	cq_index *index = NULL;
 	std::vector<cq_ctx *> ctxs;
+	// the GPU contexts come up on a thread of their own while the host decodes the index
+	std::thread ctx_thread;
+	std::vector<int> ctx_rc;
+	std::string ctx_err; // cq_last_error() is per thread: kept for the report
+	void startContexts();
 	std::vector<uint32_t> rcount_u, rcount_d; // pleafNode::rcount in file order
 };
 

@@ -25,13 +25,18 @@ for name, exe, extra in (("gpu_cli", os.path.join(REPO, "cammiq_b200", "cammiq")
     cmd = [exe, "--query", "--read_cnts", "-f", d + "/genome_map.out", "-q", fq, "-i", d + "/index_u.bin1",
            d + "/index_d.bin2", "-o", d + "/" + name + ".out"] + extra
     t = time.time()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, CAMMIQ_VERBOSE="1"))
     wall = time.time() - t
     err = r.stderr.replace("\r", "\n")
     g = lambda pat: (re.search(pat, err) or [None, None])[1]
     out[name] = {"wall_s": wall, "rc": r.returncode, "load_index_ms": g(r"Time for loading index: (\d+) ms"),
                  "query_ms": g(r"Time for query: (\d+) ms"), "nundet": g(r"unlabeled reads: (\d+)"),
-                 "nconf": g(r"conflict labels: (\d+)")}
+                 "nconf": g(r"conflict labels: (\d+)"),
+                 "verbose": [l for l in err.split("\n") if l.startswith("[cammiq]") or l.startswith("[flatten]")]}
+# FASTQ ingest alone (parallel parse + 2-bit packing), from the CLI's own diagnostic
+r = subprocess.run([os.path.join(REPO, "cammiq_b200", "cammiq"), "--dump_reads", fq], stdout=subprocess.DEVNULL,
+                   stderr=subprocess.PIPE, text=True)
+out["fastq_ingest"] = r.stderr.strip()
 out["outputs_identical"] = open(d + "/gpu_cli.out").read() == open(d + "/reference_cli.out").read()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/cli_e2e.json", "w"), indent=1)
