@@ -416,8 +416,10 @@ def run(json_fd):
         e2e_paths["host_packed_2bit"] = {"value": world * n / pk_s, "ms_per_step": pk_s * 1e3,
                                          "h2d_bytes_per_step": int(tm_pk["h2d_bytes"]), "pack_threads": pack_threads,
                                          "host_pack_ms_per_step": tm_pk["host_pack_ms"], "isa": cq.pack_isa()}
-        # the library's default on this host is the packed path; report it as the headline
-        e2e_s, h2d, e2e_path = pk_s, int(tm_pk["h2d_bytes"]), "host_packed_2bit"
+        # both are settings of the same C-ABI call (cq_ctx_set_host_packing); the headline is the
+        # faster one on this host, the other stays listed under "paths"
+        if pk_s < ascii_s:
+            e2e_s, h2d, e2e_path = pk_s, int(tm_pk["h2d_bytes"]), "host_packed_2bit"
     e2e_value = world * n / e2e_s
     d2h = (2 * (w["n_genomes"] + 1) + 4) * 8 + ((info.n_leaves_u + info.n_leaves_d) * 4 if mode == cq.MODE_P else 0)
     ctx.set_host_packing(-1)
