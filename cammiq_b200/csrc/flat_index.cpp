@@ -25,8 +25,8 @@ unsigned flattenThreads() {
 }
 
 // Insert (or find) key; returns the slot.  Linear probing by bucket.
-inline TableSlot *probeInsert(RawArray<TableSlot> &t, uint64_t mask, uint64_t key, bool &fresh) {
-	uint64_t b = mixKey(key) & mask;
+inline TableSlot *probeInsert(RawArray<TableSlot> &t, uint64_t mask, uint32_t h, uint64_t key, bool &fresh) {
+	uint64_t b = homeBucketHost(key, h, mask);
 	for (;;) {
 		TableSlot *s = &t[b * kSlotsPerBucket];
 		for (int i = 0; i < kSlotsPerBucket; i++) {
@@ -89,6 +89,26 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 	// thread.  Every key stored past its home bucket still has only full buckets before it, so
 	// lookups (stop at the first bucket with a free slot) are unaffected.
 	const unsigned T = flattenThreads();
+	// pre-pass: which thread owns each key (its home bucket's range), computed once in parallel
+	// instead of by every insert thread
+	std::vector<uint8_t> owner[2];
+	for (int t = 0; t < 2; t++) {
+		const DecodedIndex &x = t == 0 ? u : d;
+		owner[t].resize(x.bucket_key.size());
+		std::vector<std::thread> pool;
+		for (unsigned q = 0; q < T; q++)
+			pool.emplace_back([&, q, t]() {
+				const size_t a = x.bucket_key.size() * q / T, e = x.bucket_key.size() * (q + 1) / T;
+				for (size_t i = a; i < e; i++) {
+					const uint64_t b = homeBucketHost(x.bucket_key[i], u.hash_len, mask);
+					unsigned p = (unsigned) (((unsigned __int128) b * T) / nb);
+					while (p + 1 < T && b >= nb * (p + 1) / T) p++;
+					while (p > 0 && b < nb * p / T) p--;
+					owner[t][i] = (uint8_t) p;
+				}
+			});
+		for (auto &th : pool) th.join();
+	}
 	struct Deferred { uint8_t table; uint64_t index; };
 	std::vector<std::vector<Deferred>> deferred(T);
 	std::vector<uint64_t> fresh_keys(T, 0);
@@ -97,14 +117,15 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 		std::vector<std::thread> pool;
 		for (unsigned p = 0; p < T; p++)
 			pool.emplace_back([&, p]() {
-				const uint64_t lo = nb * p / T, hi = nb * (p + 1) / T;
+				const uint64_t hi = nb * (p + 1) / T;
 				for (int t = 0; t < 2; t++) {
 					const DecodedIndex &x = t == 0 ? u : d;
+					const std::vector<uint8_t> &own = owner[t];
 					for (size_t i = 0; i < x.bucket_key.size(); i++) {
-						const uint64_t key = x.bucket_key[i];
-						uint64_t b = mixKey(key) & mask;
-						if (b < lo || b >= hi)
+						if (own[i] != (uint8_t) p)
 							continue;
+						const uint64_t key = x.bucket_key[i];
+						uint64_t b = homeBucketHost(key, u.hash_len, mask);
 						if (key >= key_limit) {
 							bad_key = true;
 							continue;
@@ -152,7 +173,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 		for (const Deferred &df : deferred[p]) {
 			const DecodedIndex &x = df.table == 0 ? u : d;
 			bool fresh;
-			TableSlot *s = probeInsert(out.table, mask, x.bucket_key[df.index], fresh);
+			TableSlot *s = probeInsert(out.table, mask, u.hash_len, x.bucket_key[df.index], fresh);
 			n_keys += fresh ? 1 : 0;
 			if (df.table == 0)
 				s->u_ref = x.bucket_root[df.index];
@@ -215,7 +236,7 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), bucket == canon ? B : filterOtherPattern(B)))
 			return UINT64_MAX;
 	}
-	uint64_t b = mixKey(bucket) & mask;
+	uint64_t b = homeBucketHost(bucket, fi.hash_len, mask);
 	uint32_t ref = kRefNone;
 	for (;;) {
 		const TableSlot *s = &fi.table[b * kSlotsPerBucket];

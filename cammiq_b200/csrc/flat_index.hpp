@@ -57,19 +57,23 @@ inline uint64_t mixKey(uint64_t x) {
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
 static const uint32_t kFilterMinBitsPerKey = 8;
 
-// reverse complement of a 2-bit packed h-mer (first base most significant)
+// reverse complement of a 2-bit packed h-mer (first base most significant): complement, then
+// reverse the 32 two-bit groups (bytes, nibbles, pairs) and drop the unused low groups
 inline uint64_t revcompKeyHost(uint64_t key, uint32_t h) {
-	uint64_t x = ~key, r = 0;
-	for (uint32_t i = 0; i < h; i++) {
-		r = (r << 2) | (x & 3u);
-		x >>= 2;
-	}
-	return r;
+	uint64_t x = __builtin_bswap64(~key);
+	x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+	x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+	return x >> (64 - 2 * h);
 }
 inline uint64_t canonicalKeyHost(uint64_t key, uint32_t h) {
 	uint64_t rc = revcompKeyHost(key, h);
 	return key < rc ? key : rc;
 }
+
+// Home bucket of a key.  Keys are stored as they are, but PLACED by their canonical h-mer: a key
+// and its reverse complement share one probe sequence, so the scan -- which holds both strands'
+// hashes of a window -- finds either with ONE bucket load per read position.
+inline uint64_t homeBucketHost(uint64_t key, uint32_t h, uint64_t mask) { return mixKey(canonicalKeyHost(key, h)) & mask; }
 
 #if defined(__CUDACC__)
 __host__ __device__

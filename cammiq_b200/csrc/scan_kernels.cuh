@@ -268,7 +268,9 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 			const uint8_t *s = slotBases(p, ws, buf, slot);
 			const uint32_t rl = ws.rl[slot];
 			const unsigned long long hv = strandWindow<PACKED>(s, ws.staged != 0, rl, strand, pos, h);
-			uint64_t b = mixKey(hv) & p.table_mask;
+			// keys are placed by their canonical h-mer (flat_index.hpp, homeBucketHost)
+			const unsigned long long hv_rc = reverseGroups(~hv) >> (64 - 2 * h);
+			uint64_t b = mixKey(hv < hv_rc ? hv : hv_rc) & p.table_mask;
 			unsigned long long k0, r0, k1, r1, refs = 0;
 			bool found = false;
 			for (;;) {
@@ -461,8 +463,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 
 			uint2 ff[kStepUnroll];                                // FILTER: filter words
 			uint32_t bsel[kStepUnroll];
-			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: keys and table buckets
-			unsigned long long bf[kStepUnroll][4], br[kStepUnroll][4];
+			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: both strands' keys and their shared bucket
+			unsigned long long bk[kStepUnroll][4];
 #pragma unroll
 			for (int u = 0; u < kStepUnroll; u++) {
 				const uint32_t j = j0 + u;
@@ -484,8 +486,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 					} else {
 						kf[u] = hf;
 						kr[u] = hr;
-						loadBucket(p.table + 2 * (mixKey(hf) & p.table_mask), bf[u][0], bf[u][1], bf[u][2], bf[u][3]);
-						loadBucket(p.table + 2 * (mixKey(hr) & p.table_mask), br[u][0], br[u][1], br[u][2], br[u][3]);
+						// a key and its reverse complement share their home bucket: one sector per position
+						loadBucket(p.table + 2 * (mixKey(hf < hr ? hf : hr) & p.table_mask), bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
 					}
 				}
 			}
@@ -506,8 +508,9 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							cand_r = (fwd_canon && !palin) ? other : same;
 						} else {
 							// candidate = the bucket holds the key, or is full and the key may have spilled
-							cand_f = bf[u][0] == kf[u] || bf[u][2] == kf[u] || (bf[u][0] != kEmptyKey && bf[u][2] != kEmptyKey);
-							cand_r = br[u][0] == kr[u] || br[u][2] == kr[u] || (br[u][0] != kEmptyKey && br[u][2] != kEmptyKey);
+							const bool full = bk[u][0] != kEmptyKey && bk[u][2] != kEmptyKey;
+							cand_f = bk[u][0] == kf[u] || bk[u][2] == kf[u] || full;
+							cand_r = bk[u][0] == kr[u] || bk[u][2] == kr[u] || full;
 						}
 					}
 					if (p.debug_flags & 2u) {

@@ -38,12 +38,23 @@ ctx = cq.Context(0).upload(idx, G)
 out["upload_s"] = time.time() - t
 reads, src = sl.make_reads(p, 0, n, rl, 0.01, want_src=True)
 lengths = np.full(n, rl, dtype=np.uint8)
-a = ctx.query(cq.MODE_P, reads.reshape(-1), None, lengths, stride=rl, per_read=True)
-tm = ctx.timing()
+# kernel time: reads resident in HBM, second launch
+ctx.stage(reads.reshape(-1), None, lengths, stride=rl)
+for _ in range(2):
+    ctx.reset()
+    ctx.query_staged(cq.MODE_P)
+    ctx.sync()
+    tm = ctx.timing()
 out["scan_ms"] = tm["scan_ms"]
 out["reads_per_s_kernel"] = n / (tm["scan_ms"] * 1e-3)
-out["probes_per_s"] = tm["probes"] / (tm["scan_ms"] * 1e-3)
+out["table_sectors_per_s_phase1"] = (tm["probes"] / 2) / (tm["scan_ms"] * 1e-3)
+out["chained_loads"] = tm["chained_loads"]
 ctx.reset()
+for _ in range(2):
+    t = time.time()
+    a = ctx.query(cq.MODE_P, reads.reshape(-1), None, lengths, stride=rl, per_read=True)
+    out["e2e_query_ms_with_per_read_outputs"] = (time.time() - t) * 1e3
+    ctx.reset()
 lut = np.arange(256, dtype=np.uint8)
 for x, y in zip(b"ACGT", b"TGCA"):
     lut[x] = y
