@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 
 			uint2 ff[kStepUnroll];                                // FILTER: filter words
 			uint32_t bsel[kStepUnroll];
-			unsigned long long kf[kStepUnroll], kr[kStepUnroll];  // !FILTER: both strands' keys and their shared bucket
+			unsigned long long kf[kStepUnroll];                   // !FILTER: the forward key and the strands' shared bucket
 			unsigned long long bk[kStepUnroll][4];
 #pragma unroll
 			for (int u = 0; u < kStepUnroll; u++) {
@@ -485,7 +485,6 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_shift), pol_keep);
 					} else {
 						kf[u] = hf;
-						kr[u] = hr;
 						// a key and its reverse complement share their home bucket: one sector per position
 						loadBucket(p.table + 2 * (mixKey(hf < hr ? hf : hr) & p.table_mask), bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
 					}
@@ -508,9 +507,11 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							cand_r = (fwd_canon && !palin) ? other : same;
 						} else {
 							// candidate = the bucket holds the key, or is full and the key may have spilled
+							// the reverse strand's key is recomputed rather than kept live across the loads
+							const unsigned long long kr = reverseGroups(~kf[u]) >> (64 - 2 * h);
 							const bool full = bk[u][0] != kEmptyKey && bk[u][2] != kEmptyKey;
 							cand_f = bk[u][0] == kf[u] || bk[u][2] == kf[u] || full;
-							cand_r = bk[u][0] == kr[u] || bk[u][2] == kr[u] || full;
+							cand_r = bk[u][0] == kr || bk[u][2] == kr || full;
 						}
 					}
 					if (p.debug_flags & 2u) {
