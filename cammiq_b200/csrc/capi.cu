@@ -258,11 +258,17 @@ static void freeDevice(cq_ctx *c) {
 	c->has_index = false;
 }
 
-// CAMMIQ_PACK_THREADS if set, else min(16, hardware threads) on hosts with at least 4, else 0
+// CAMMIQ_PACK_THREADS if set, else min(16, hardware threads) on hosts with at least 4, else 0.
+// Packing trades PCIe bytes for host memory traffic; with several ranks on one host
+// (LOCAL_WORLD_SIZE > 1, one process per GPU) the host's memory system is the shared bottleneck
+// and plain DMA of the ASCII reads is faster (measured at 2 ranks), so the default is off there.
 static int defaultPackThreads() {
 	const char *env = getenv("CAMMIQ_PACK_THREADS");
 	if (env != NULL)
 		return std::max(0, atoi(env));
+	const char *lws = getenv("LOCAL_WORLD_SIZE");
+	if (lws != NULL && atoi(lws) > 1)
+		return 0;
 	const unsigned hw = std::thread::hardware_concurrency();
 	return hw >= 4 ? (int) std::min(hw, 16u) : 0;
 }

@@ -198,8 +198,9 @@ int cq_query(cq_ctx *ctx, int mode, const uint8_t *bases, const uint64_t *offset
  * cq_query converts each chunk of reads to 2-bit codes with `threads` host threads (AVX-512 /
  * AVX2 / scalar), validates them there, and overlaps pack -> copy -> scan chunk by chunk.
  * Results are identical either way.  threads = 0 turns packing off (ASCII crosses PCIe, the
- * kernel decodes); threads < 0 restores the default: CAMMIQ_PACK_THREADS if set, else
- * min(16, hardware threads) when the host has at least 4, else off.
+ * kernel decodes); threads < 0 restores the default: CAMMIQ_PACK_THREADS if set, else off when
+ * LOCAL_WORLD_SIZE > 1 (several ranks share the host's memory bandwidth, which is what packing
+ * spends), else min(16, hardware threads) when the host has at least 4, else off.
  */
 int cq_ctx_set_host_packing(cq_ctx *ctx, int threads);
 
