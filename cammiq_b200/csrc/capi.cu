@@ -64,7 +64,7 @@ struct cq_ctx {
 	uint32_t *d_partials = NULL;
 	uint32_t *d_spill = NULL; // per-read hit overflow, [max grid warps][32][kHitSpill]
 	uint2 *d_filter = NULL;
-	uint32_t filter_shift = 0;
+	uint32_t filter_words = 0;
 	int max_grid = 0;
 	unsigned long long *d_probe_count = NULL;
 	int grid = 0;
@@ -389,7 +389,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 
 	if (!f.filter.empty()) {
 		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), c->stream)) != 0) return rc;
-		c->filter_shift = f.filter_shift;
+		c->filter_words = f.filter_words;
 		CQ_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	// block-private genome counters in shared memory when they fit, global atomics otherwise;
@@ -532,7 +532,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.h = c->h;
 	sp.n_genomes = c->n_genomes;
 	sp.filter = c->d_filter;
-	sp.filter_shift = c->filter_shift;
+	sp.filter_words = c->filter_words;
 	sp.bases = rb.bases;
 	sp.offsets = rb.offsets;
 	sp.offsets32 = rb.offsets32;

@@ -196,17 +196,15 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 	fi.filter.shrink_to_fit();
 	if (max_bytes < 8192)
 		return;
-	// 16 bits per key when they fit, never fewer than kFilterMinBitsPerKey
-	uint64_t words = 1024;
-	while (words * 64 < fi.n_keys * 16 && words * 8 * 2 <= max_bytes && words < (1ull << 31))
-		words <<= 1;
+	// 16 bits per key when the budget allows, never fewer than kFilterMinBitsPerKey
+	uint64_t words = std::max<uint64_t>(1024, (fi.n_keys * 16 + 63) / 64);
+	words = std::min<uint64_t>(words, max_bytes / 8);
+	words = std::min<uint64_t>(words, (1ull << 31));
+	words &= ~127ull; // whole 1 KB blocks
 	if (words * 64 < fi.n_keys * kFilterMinBitsPerKey)
 		return; // would not fit L2 at a useful false-positive rate: probe the table directly
 	fi.filter.assign(words, 0);
-	uint32_t bits = 0;
-	while ((1ull << bits) < words)
-		bits++;
-	fi.filter_shift = 32 - bits;
+	fi.filter_words = (uint32_t) words;
 	const unsigned T = flattenThreads();
 	std::vector<std::thread> pool;
 	for (unsigned p = 0; p < T; p++)
@@ -218,7 +216,7 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 				uint32_t A, B;
 				const uint64_t key = fi.table[i].key, canon = canonicalKeyHost(key, fi.hash_len);
 				filterHash(canon, A, B);
-				__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_shift)],
+				__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_words)],
 					filterMask(key == canon ? B : filterOtherPattern(B)), __ATOMIC_RELAXED);
 			}
 		});
@@ -232,7 +230,7 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 		uint32_t A, B;
 		const uint64_t canon = canonicalKeyHost(bucket, fi.hash_len);
 		filterHash(canon, A, B);
-		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_shift)];
+		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_words)];
 		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), bucket == canon ? B : filterOtherPattern(B)))
 			return UINT64_MAX;
 	}

@@ -95,11 +95,17 @@ inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
 __host__ __device__
 #endif
 inline uint32_t filterOtherPattern(uint32_t B) { return (B >> 12) * 0x2C1B3C6Du + 0x9E3779B9u; } // only the selector bits of B
-// word index for a filter of 2^(32 - shift) words
+// word index for a filter of `words` words (any count below 2^32): the high half of A * words
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline uint32_t filterWordIndex(uint32_t A, uint32_t shift) { return A >> shift; }
+inline uint32_t filterWordIndex(uint32_t A, uint32_t words) {
+#if defined(__CUDA_ARCH__)
+	return __umulhi(A, words);
+#else
+	return (uint32_t) (((uint64_t) A * words) >> 32);
+#endif
+}
 // all four selected bits set in the word (x = low half, y = high half)?
 #if defined(__CUDACC__)
 __host__ __device__
@@ -145,7 +151,7 @@ struct FlatIndex {
 	uint64_t n_keys = 0;
 	RawArray<TableSlot> table;    // n_table_buckets * kSlotsPerBucket
 	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
-	uint32_t filter_shift = 0;    // 32 - log2(filter words)
+	uint32_t filter_words = 0;    // = filter.size()
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
 	double decode_ms = 0, flatten_ms = 0;
 

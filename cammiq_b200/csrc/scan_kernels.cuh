@@ -43,7 +43,7 @@ struct ScanParams {
 	const TableSlot *table;
 	uint64_t table_mask;
 	const uint2 *filter;      // NULL: no filter, phase 1 probes the table
-	uint32_t filter_shift;    // 32 - log2(filter words)
+	uint32_t filter_words;    // number of 64-bit filter words
 	const uint32_t *nodes_u, *nodes_d;
 	const uint32_t *leaf_u_ref;
 	const uint2 *leaf_d_ref;
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 						if (p.debug_flags & 4u)
 							ff[u] = make_uint2(a, bsel[u]);
 						else
-							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_shift), pol_keep);
+							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
 					} else {
 						kf[u] = hf;
 						// a key and its reverse complement share their home bucket: one sector per position
