@@ -545,10 +545,6 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	const uint32_t read_bytes = rb.packed ? (std::max<uint32_t>(rb.max_len, 1) + 3) / 4 : std::max<uint32_t>(rb.max_len, 1);
 	const uint32_t tile_cap = (32 * read_bytes + (rb.packed ? 64 : 32) + 127) & ~127u;
 	sp.tile_cap = tile_cap;
-	{
-		const char *dbg = getenv("CAMMIQ_DEBUG_FLAGS");
-		sp.debug_flags = dbg ? (uint32_t) atoi(dbg) : 0u;
-	}
 	const size_t dyn_smem = (size_t) kWarpsPerBlock * tile_cap + c->smem_bytes;
 	sp.smem_counters = c->smem_counters ? 1 : 0;
 	sp.partials = c->d_partials;

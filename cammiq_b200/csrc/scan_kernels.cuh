@@ -61,7 +61,6 @@ struct ScanParams {
 	const uint8_t *lengths;
 	uint64_t n_reads;
 	uint32_t tile_cap;        // bytes of one staging buffer (32 reads); 2 per warp
-	uint32_t debug_flags;     // experiments only (CAMMIQ_DEBUG_FLAGS): 1 plain filter loads, 2 skip phases 2+3, 4 no filter loads
 	// outputs
 	int smem_counters;        // 1: block-private genome counters + partials, 0: global atomics
 	uint32_t *partials;       // [gridDim.x][2*(G+1)]
@@ -479,10 +478,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 						filterHash(hf < hr ? hf : hr, a, bsel[u]);
 						// the two lowest bits of B are unused by the selectors: remember the orientation
 						bsel[u] = (bsel[u] & ~3u) | (hf <= hr ? 1u : 0u) | (hf == hr ? 2u : 0u);
-						if (p.debug_flags & 4u)
-							ff[u] = make_uint2(a, bsel[u]);
-						else
-							ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
+						ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
 					} else {
 						kf[u] = hf;
 						// a key and its reverse complement share their home bucket: one sector per position
@@ -513,10 +509,6 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							cand_f = bk[u][0] == kf[u] || bk[u][2] == kf[u] || full;
 							cand_r = bk[u][0] == kr || bk[u][2] == kr || full;
 						}
-					}
-					if (p.debug_flags & 2u) {
-						n_cand += cand_f + cand_r;
-						cand_f = cand_r = false;
 					}
 					if (cand_f) {
 						// forward strand, position i = j-h+1
