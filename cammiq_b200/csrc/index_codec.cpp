@@ -1,7 +1,17 @@
 #include "index_codec.hpp"
 
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/cammiq_gpu.h"
 
@@ -18,19 +28,6 @@ int baseCode(uint8_t c) {
 }
 
 namespace {
-
-bool slurp(const std::string &fn, std::vector<uint8_t> &buf) {
-	FILE *f = fopen(fn.c_str(), "rb");
-	if (f == NULL)
-		return false;
-	fseek(f, 0, SEEK_END);
-	long n = ftell(f);
-	fseek(f, 0, SEEK_SET);
-	buf.resize((size_t) n);
-	bool ok = (n == 0) || fread(buf.data(), 1, (size_t) n, f) == (size_t) n;
-	fclose(f);
-	return ok;
-}
 
 // MSB-first bit cursor over the AUX stream; reads past the end return 1 (the reference
 // reader yields all-ones there, binaryio.cpp:146-149).
@@ -62,74 +59,199 @@ struct BitCursor {
 	}
 };
 
-struct ByteCursor {
-	const uint8_t *p;
-	uint64_t n, pos;
-	bool overrun;
-	// fast paths for the common widths (unaligned load + byte swap), with the same overrun rule
-	inline uint64_t be8() {
-		if (pos + 8 <= n) {
-			uint64_t v;
-			memcpy(&v, p + pos, 8);
-			pos += 8;
-			return __builtin_bswap64(v);
-		}
-		return be(8);
-	}
-	inline uint32_t be4() {
-		if (pos + 4 <= n) {
-			uint32_t v;
-			memcpy(&v, p + pos, 4);
-			pos += 4;
-			return __builtin_bswap32(v);
-		}
-		return (uint32_t) be(4);
-	}
-	inline uint16_t be2() {
-		if (pos + 2 <= n) {
-			uint16_t v = (uint16_t) ((p[pos] << 8) | p[pos + 1]);
-			pos += 2;
-			return v;
-		}
-		return (uint16_t) be(2);
-	}
-	inline uint64_t be(int nbytes) {
-		uint64_t v = 0;
-		for (int i = 0; i < nbytes; i++) {
-			uint8_t b = 0xFF;
-			if (pos < n)
-				b = p[pos];
-			else
-				overrun = true;
-			pos++;
-			v = (v << 8) | b;
-		}
-		return v;
-	}
-};
-
 struct Frame {
-	uint32_t node;  // index into nodes (provisional)
+	uint32_t node;  // id of this node (provisional until a child turns up)
 	uint8_t next;   // next child slot to decode
 	uint8_t depth;  // trie depth of this node (uint8 arithmetic like the reference)
 	bool any;       // some child was non-NULL
 };
 
+// A whole file mapped read-only (falls back to reading it when it cannot be mapped).
+struct FileView {
+	const uint8_t *p = NULL;
+	uint64_t n = 0;
+	bool mapped = false;
+	std::vector<uint8_t> owned;
+	~FileView() {
+		if (mapped && p != NULL)
+			munmap((void *) p, n);
+	}
+	bool open(const std::string &fn) {
+		int fd = ::open(fn.c_str(), O_RDONLY);
+		if (fd < 0)
+			return false;
+		struct stat st;
+		if (fstat(fd, &st) != 0) {
+			close(fd);
+			return false;
+		}
+		n = (uint64_t) st.st_size;
+		if (n > 0) {
+			void *m = mmap(NULL, n, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED) {
+				p = (const uint8_t *) m;
+				mapped = true;
+				madvise(m, n, MADV_WILLNEED);
+			} else {
+				owned.resize(n);
+				uint64_t got = 0;
+				while (got < n) {
+					ssize_t r = read(fd, owned.data() + got, n - got);
+					if (r <= 0)
+						break;
+					got += (uint64_t) r;
+				}
+				if (got != n) {
+					close(fd);
+					return false;
+				}
+				p = owned.data();
+			}
+		}
+		close(fd);
+		return true;
+	}
+};
+
+// The trie shape of one bucket is a pre-order bit string: '0' = no child, '1' + four children =
+// a node, and a node whose four children are all absent is a leaf (hashtrie.cpp:432-457).  The
+// walker below is shared by the two passes of the decoder through a sink:
+//   CountSink   pass 1, one thread: how many leaves / internal nodes precede every bucket
+//   StoreSink   pass 2, all threads: fills the flat arrays of a bucket range
+struct CountSink {
+	uint64_t leaves = 0, nodes = 0;
+	inline uint32_t newNode() { return (uint32_t) nodes++; }
+	inline void dropLastNode() { nodes--; }
+	inline uint32_t leaf(uint8_t) { return kRefLeafTag | (uint32_t) leaves++; }
+	inline void setChild(uint32_t, uint8_t, uint32_t) {}
+};
+
+struct StoreSink {
+	DecodedIndex *out;
+	const uint8_t *ints; // INT stream
+	uint64_t int_size;
+	uint64_t bucket;     // bucket being decoded: its leaf records follow its key
+	uint64_t leaves, nodes;
+	uint32_t leaf_bytes, h;
+	bool dd, bad_pair = false;
+	uint32_t max_ref = 0;
+	inline uint32_t newNode() {
+		uint32_t *c = &out->nodes[4 * (size_t) nodes];
+		c[0] = c[1] = c[2] = c[3] = kRefNone;
+		return (uint32_t) nodes++;
+	}
+	inline void dropLastNode() { nodes--; }
+	inline uint32_t leaf(uint8_t depth) {
+		const uint64_t id = leaves++;
+		const uint8_t *r = ints + 8 * (bucket + 1) + (uint64_t) leaf_bytes * id; // pass 1 checked the extent
+		uint32_t r1, r2 = 0;
+		uint16_t c1, c2 = 0;
+		memcpy(&r1, r, 4);
+		r1 = __builtin_bswap32(r1);
+		if (dd) {
+			memcpy(&r2, r + 4, 4);
+			r2 = __builtin_bswap32(r2);
+			c1 = (uint16_t) ((r[8] << 8) | r[9]);
+			c2 = (uint16_t) ((r[10] << 8) | r[11]);
+			bad_pair |= r1 == 0 || r2 == 0;
+		} else
+			c1 = (uint16_t) ((r[4] << 8) | r[5]);
+		out->ref_id1[id] = r1;
+		out->ref_id2[id] = r2;
+		out->ucount1[id] = c1;
+		out->ucount2[id] = c2;
+		out->depth[id] = (uint8_t) (depth + h);
+		max_ref = std::max(max_ref, std::max(r1, r2));
+		return kRefLeafTag | (uint32_t) id;
+	}
+	inline void setChild(uint32_t node, uint8_t slot, uint32_t ref) { out->nodes[4 * (size_t) node + slot] = ref; }
+};
+
+// Decodes the shape of one bucket; returns its root reference, or false on a runaway stream.
+template <class Sink>
+inline bool walkBucket(BitCursor &bc, Sink &sk, std::vector<Frame> &stack, uint32_t &root) {
+	root = kRefNone;
+	// fast path: the bucket is one leaf at depth h ("10000")
+	if (bc.peek5() == 0x10u) {
+		bc.pos += 5;
+		root = sk.leaf(0);
+		return true;
+	}
+	if (bc.bit() == 0)
+		return true;
+	stack.clear();
+	Frame f0 = {sk.newNode(), 0, 0, false};
+	stack.push_back(f0);
+	while (!stack.empty()) {
+		Frame &f = stack.back();
+		if (f.next < 4) {
+			uint8_t slot = f.next++;
+			if (bc.peek5() == 0x10u) {
+				bc.pos += 5;
+				f.any = true;
+				sk.setChild(f.node, slot, sk.leaf((uint8_t) (f.depth + 1)));
+			} else if (bc.bit() != 0) {
+				if (stack.size() > 4096 || bc.pos > bc.nbits + 64)
+					return false;
+				f.any = true;
+				const uint8_t d1 = (uint8_t) (f.depth + 1);
+				const uint32_t parent = f.node, id = sk.newNode();
+				sk.setChild(parent, slot, id + 1);
+				Frame nf = {id, 0, d1, false};
+				stack.push_back(nf); // invalidates f
+			}
+			continue;
+		}
+		// all four children decoded
+		Frame done = f;
+		stack.pop_back();
+		if (!done.any) {
+			// a node with four NULL children is a leaf; it is the most recently created node, so
+			// it can be dropped from the node array
+			sk.dropLastNode();
+			uint32_t lr = sk.leaf(done.depth);
+			if (stack.empty())
+				root = lr;
+			else {
+				Frame &p = stack.back();
+				sk.setChild(p.node, (uint8_t) (p.next - 1), lr);
+			}
+		} else if (stack.empty())
+			root = done.node + 1;
+	}
+	return true;
+}
+
+struct Checkpoint {
+	uint64_t aux_pos, leaves, nodes;
+};
+static const uint64_t kCheckpointBuckets = 4096;
+
+unsigned decodeThreads() {
+	const char *env = getenv("CAMMIQ_DECODE_THREADS");
+	unsigned n = env ? (unsigned) atoi(env) : std::thread::hardware_concurrency();
+	return std::max(1u, std::min(n, 16u));
+}
+
 } // namespace
 
+// Two passes.  Pass 1 walks the AUX bit stream alone on one thread (the stream is strictly
+// sequential) and records, every 4096 buckets, the bit position and the number of leaves and
+// internal nodes so far; that also fixes every bucket's position in the INT stream
+// (8 bytes of key per bucket + one fixed-size record per leaf).  Pass 2 decodes the bucket
+// ranges between checkpoints on all threads straight into the pre-sized flat arrays; ids are
+// file order either way.
 int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err) {
-	std::vector<uint8_t> ibuf, abuf;
-	if (!slurp(path, ibuf)) {
+	FileView ints, aux;
+	if (!ints.open(path)) {
 		err = "Cannot open file: " + path + ".";
 		return CQ_EIO;
 	}
-	if (!slurp(path + ".aux", abuf)) {
+	if (!aux.open(path + ".aux")) {
 		err = "Cannot open file: " + path + ".aux.";
 		return CQ_EIO;
 	}
-	BitCursor bc = {abuf.data(), (uint64_t) abuf.size() * 8, 0};
-	ByteCursor ic = {ibuf.data(), (uint64_t) ibuf.size(), 0, false};
-
+	BitCursor bc = {aux.p, aux.n * 8, 0};
 	out = DecodedIndex();
 	out.doubly_unique = bc.bit() != 0;
 	uint32_t option = bc.bits(7);
@@ -143,120 +265,111 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 		return CQ_EFORMAT;
 	}
 	const bool dd = out.doubly_unique;
-	const uint32_t h = out.hash_len;
-	// size hint: one leaf record is 6 or 12 bytes, almost every bucket is a single leaf
-	size_t hint = ibuf.size() / (dd ? 20 : 14) + 16;
-	out.bucket_key.reserve(hint);
-	out.bucket_root.reserve(hint);
-	out.ref_id1.reserve(hint);
-	out.ucount1.reserve(hint);
-	out.depth.reserve(hint);
-	if (dd) {
-		out.ref_id2.reserve(hint);
-		out.ucount2.reserve(hint);
-	}
+	const uint32_t h = out.hash_len, leaf_bytes = dd ? 12 : 6;
 
-	auto readLeaf = [&](uint8_t depth) -> uint32_t {
-		uint32_t id = (uint32_t) out.ref_id1.size();
-		uint32_t r1 = ic.be4(), r2 = 0;
-		uint16_t c1, c2 = 0;
-		if (dd) {
-			r2 = ic.be4();
-			c1 = ic.be2();
-			c2 = ic.be2();
-		} else
-			c1 = ic.be2();
-		out.ref_id1.push_back(r1);
-		out.ref_id2.push_back(r2);
-		out.ucount1.push_back(c1);
-		out.ucount2.push_back(c2);
-		out.depth.push_back((uint8_t) (depth + h));
-		if (r1 > out.max_ref_id) out.max_ref_id = r1;
-		if (r2 > out.max_ref_id) out.max_ref_id = r2;
-		return kRefLeafTag | id;
-	};
-
+	auto t_start = std::chrono::high_resolution_clock::now();
+	// ---- pass 1: shape only
+	std::vector<Checkpoint> cps;
+	cps.reserve((size_t) (ints.n / (8 + leaf_bytes) / kCheckpointBuckets + 2));
+	CountSink cs;
 	std::vector<Frame> stack;
-	uint64_t key = ic.be8();
-	while (key != UINT64_MAX) {
-		if (ic.overrun) {
+	uint64_t buckets = 0;
+	for (;;) {
+		const uint64_t at = 8 * buckets + (uint64_t) leaf_bytes * cs.leaves;
+		if (at + 8 > ints.n) {
 			err = "Index " + path + ": INT stream ends before the END64 terminator.";
 			return CQ_EFORMAT;
 		}
-		uint32_t root = kRefNone;
-		// fast path: the bucket is one leaf at depth h ("10000")
-		if (bc.peek5() == 0x10u) {
-			bc.pos += 5;
-			root = readLeaf(0);
-		} else if (bc.bit() != 0) {
-			stack.clear();
-			out.nodes.insert(out.nodes.end(), 4, kRefNone);
-			Frame f0 = {(uint32_t) (out.nodes.size() / 4 - 1), 0, 0, false};
-			stack.push_back(f0);
-			while (!stack.empty()) {
-				Frame &f = stack.back();
-				if (f.next < 4) {
-					uint8_t slot = f.next++;
-					if (bc.peek5() == 0x10u) {
-						bc.pos += 5;
-						uint32_t lr = readLeaf((uint8_t) (f.depth + 1));
-						out.nodes[4 * (size_t) f.node + slot] = lr;
-						f.any = true;
-					} else if (bc.bit() != 0) {
-						if (stack.size() > 4096 || bc.pos > bc.nbits + 64) {
-							err = "Index " + path + ": AUX stream is malformed (runaway trie).";
-							return CQ_EFORMAT;
-						}
-						f.any = true;
-						uint8_t d1 = (uint8_t) (f.depth + 1);
-						uint32_t parent = f.node;
-						out.nodes.insert(out.nodes.end(), 4, kRefNone);
-						uint32_t id = (uint32_t) (out.nodes.size() / 4 - 1);
-						out.nodes[4 * (size_t) parent + slot] = id + 1;
-						Frame nf = {id, 0, d1, false};
-						stack.push_back(nf); // invalidates f
-					}
-					continue;
-				}
-				// all four children decoded
-				Frame done = f;
-				stack.pop_back();
-				if (!done.any) {
-					// a node with four NULL children is a leaf (hashtrie.cpp:432-457); it is the
-					// most recently created node, so it can be dropped from the node array
-					out.nodes.resize(out.nodes.size() - 4);
-					uint32_t lr = readLeaf(done.depth);
-					if (stack.empty())
-						root = lr;
-					else {
-						Frame &p = stack.back();
-						out.nodes[4 * (size_t) p.node + (p.next - 1)] = lr;
-					}
-				} else if (stack.empty())
-					root = done.node + 1;
-			}
+		uint64_t key;
+		memcpy(&key, ints.p + at, 8);
+		if (key == UINT64_MAX)
+			break;
+		if (buckets % kCheckpointBuckets == 0) {
+			Checkpoint c = {bc.pos, cs.leaves, cs.nodes};
+			cps.push_back(c);
 		}
-		if (dd && root != kRefNone) {
-			// doubly-unique leaves must carry two ids (assert at hashtrie.cpp:446)
+		uint32_t root;
+		if (!walkBucket(bc, cs, stack, root) || bc.pos > bc.nbits + 64) {
+			err = "Index " + path + ": AUX stream is malformed (runaway trie).";
+			return CQ_EFORMAT;
 		}
-		out.bucket_key.push_back(key);
-		out.bucket_root.push_back(root);
-		key = ic.be8();
-		if (out.ref_id1.size() >= 0x7FFFFFF0ull || out.nodes.size() / 4 >= 0x7FFFFFF0ull) {
+		buckets++;
+		if (cs.leaves >= 0x7FFFFFF0ull || cs.nodes >= 0x7FFFFFF0ull) {
 			err = "Index " + path + ": more than 2^31 leaves or nodes.";
 			return CQ_EFORMAT;
 		}
 	}
-	if (ic.overrun) {
-		err = "Index " + path + ": INT stream truncated.";
+	const uint64_t n_leaves = cs.leaves, n_nodes = cs.nodes;
+	auto t_pass1 = std::chrono::high_resolution_clock::now();
+	out.bucket_key.resize((size_t) buckets);
+	out.bucket_root.resize((size_t) buckets);
+	out.nodes.resize((size_t) n_nodes * 4);
+	out.ref_id1.resize((size_t) n_leaves);
+	out.ref_id2.resize((size_t) n_leaves);
+	out.ucount1.resize((size_t) n_leaves);
+	out.ucount2.resize((size_t) n_leaves);
+	out.depth.resize((size_t) n_leaves);
+
+	// ---- pass 2: fill, one checkpoint range at a time per thread
+	const unsigned T = (unsigned) std::min<uint64_t>(decodeThreads(), std::max<uint64_t>(1, cps.size()));
+	std::atomic<size_t> next(0);
+	std::vector<uint32_t> max_ref(T, 0);
+	std::atomic<bool> bad_pair(false), broken(false);
+	auto work = [&](unsigned t) {
+		std::vector<Frame> st;
+		for (;;) {
+			const size_t c = next.fetch_add(1);
+			if (c >= cps.size())
+				break;
+			BitCursor b2 = {aux.p, aux.n * 8, cps[c].aux_pos};
+			StoreSink sk;
+			sk.out = &out;
+			sk.ints = ints.p;
+			sk.int_size = ints.n;
+			sk.leaves = cps[c].leaves;
+			sk.nodes = cps[c].nodes;
+			sk.leaf_bytes = leaf_bytes;
+			sk.h = h;
+			sk.dd = dd;
+			const uint64_t lo = (uint64_t) c * kCheckpointBuckets, hi = std::min(buckets, lo + kCheckpointBuckets);
+			for (uint64_t b = lo; b < hi; b++) {
+				uint64_t key;
+				memcpy(&key, ints.p + 8 * b + (uint64_t) leaf_bytes * sk.leaves, 8);
+				sk.bucket = b;
+				uint32_t root;
+				if (!walkBucket(b2, sk, st, root)) {
+					broken = true;
+					return;
+				}
+				out.bucket_key[(size_t) b] = __builtin_bswap64(key);
+				out.bucket_root[(size_t) b] = root;
+			}
+			max_ref[t] = std::max(max_ref[t], sk.max_ref);
+			if (sk.bad_pair)
+				bad_pair = true;
+		}
+	};
+	{
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < T; t++)
+			pool.emplace_back(work, t);
+		work(0);
+		for (auto &th : pool) th.join();
+	}
+	if (getenv("CAMMIQ_VERBOSE"))
+		fprintf(stderr, "[decode] %s: %lu buckets, shape pass %.0f ms, fill pass %.0f ms on %u threads\n", path.c_str(),
+			(unsigned long) buckets, std::chrono::duration<double, std::milli>(t_pass1 - t_start).count(),
+			std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t_pass1).count(), T);
+	if (broken) {
+		err = "Index " + path + ": AUX stream is malformed (runaway trie).";
 		return CQ_EFORMAT;
 	}
-	if (dd)
-		for (size_t i = 0; i < out.ref_id1.size(); i++)
-			if (out.ref_id1[i] == 0 || out.ref_id2[i] == 0) {
-				err = "Index " + path + ": doubly-unique leaf without two genome ids.";
-				return CQ_EFORMAT;
-			}
+	for (unsigned t = 0; t < T; t++)
+		out.max_ref_id = std::max(out.max_ref_id, max_ref[t]);
+	if (dd && bad_pair) {
+		err = "Index " + path + ": doubly-unique leaf without two genome ids.";
+		return CQ_EFORMAT;
+	}
 	return CQ_OK;
 }
 

@@ -64,6 +64,41 @@ def test_decode_matches_oracle(case):
         assert np.array_equal(off, ooff) and np.array_equal(ids, oids)
 
 
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_parallel_decode_of_many_buckets_matches_oracle(tmp_path, threads, monkeypatch):
+    """The decoder's second pass fills 4096-bucket ranges in parallel from checkpoints of the
+    first; an index with ~150 such ranges, a fifth of its keys deeper than h (tries that straddle
+    range ends), against the oracle's sequential recursive decoder: every leaf field, the
+    per-genome leaf lists in file order, and lookups that descend the tries."""
+    from cammiq_b200 import synthlib as sl
+    monkeypatch.setenv("CAMMIQ_DECODE_THREADS", threads)
+    p = sl.params(seed=31, n_genomes=40, genome_len=400_000, cluster_size=4, permille_deep=200)
+    sl.write_index(p, str(tmp_path))
+    iu, idd = str(tmp_path / "index_u.bin1"), str(tmp_path / "index_d.bin2")
+    idx = cq.Index(iu, idd)
+    assert idx.info.n_buckets_u > 20 * 4096 and idx.info.n_nodes_u > 10000
+    rng = np.random.default_rng(1)
+    reads = sl.make_reads(p, 0, 300, 120, 0.0)
+    for table, path in ((cq.TABLE_U, iu), (cq.TABLE_D, idd)):
+        oi = ol.OracleIndex(path)
+        lv = idx.leaves(table)
+        for mine, ref in (("ref_id1", oi.ref1), ("ref_id2", oi.ref2), ("ucount1", oi.ucount1),
+                          ("ucount2", oi.ucount2), ("depth", oi.depth)):
+            assert np.array_equal(lv[mine], ref), (table, mine)
+        off, ids = idx.map_sp(table, 40)
+        ooff, oids = oi.map_sp(40)
+        assert np.array_equal(off, ooff) and np.array_equal(ids, oids)
+        h, hits = idx.hash_len, 0
+        for r in reads:
+            r = r.tobytes()
+            for i in rng.integers(0, len(r) - h, 40):
+                key = ol.lib().cqo_hash(r[i:i + h], h)
+                want = oi.find(key, r[i + h:])
+                assert idx.find_host(table, key, r[i + h:]) == want
+                hits += want != ol.NONE
+        assert hits > 20
+
+
 @pytest.mark.parametrize("case", golden_cases())
 @pytest.mark.parametrize("load_factor", [0.0, 0.95])
 def test_flat_lookup_matches_oracle_find(case, load_factor):
