@@ -345,12 +345,59 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	delete c;
 }
 
+// The index arrays live in pageable memory; a plain cudaMemcpy of them is staged by the driver
+// on one thread (~5 GB/s).  Large arrays go through two pinned buffers filled by a few host
+// threads instead, so the copy engine sees pinned memory and runs near PCIe speed.
+struct Uploader {
+	static const size_t kChunk = 32u << 20;
+	cudaStream_t st;
+	WorkerPool pool;
+	uint8_t *stage[2] = {NULL, NULL};
+	cudaEvent_t ev[2] = {NULL, NULL};
+	uint64_t k = 0;
+	explicit Uploader(cudaStream_t s) : st(s), pool((int) std::max(1u, std::min(std::thread::hardware_concurrency(), 8u))) {}
+	~Uploader() {
+		cudaStreamSynchronize(st);
+		for (int i = 0; i < 2; i++) {
+			if (stage[i]) cudaFreeHost(stage[i]);
+			if (ev[i]) cudaEventDestroy(ev[i]);
+		}
+	}
+	int copy(void *dst, const void *src, size_t bytes) {
+		if (bytes < (4u << 20)) {
+			CQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+			return CQ_OK;
+		}
+		for (int i = 0; i < 2; i++)
+			if (stage[i] == NULL) {
+				CQ_CUDA(cudaHostAlloc((void **) &stage[i], kChunk, cudaHostAllocDefault));
+				CQ_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+			}
+		const int T = pool.size();
+		for (size_t off = 0; off < bytes; off += kChunk, k++) {
+			const int b = (int) (k & 1);
+			const size_t n = std::min(kChunk, bytes - off);
+			if (k >= 2)
+				CQ_CUDA(cudaEventSynchronize(ev[b]));
+			const uint8_t *from = (const uint8_t *) src + off;
+			uint8_t *to = stage[b];
+			pool.run([&](int t) {
+				const size_t lo = n * (size_t) t / (size_t) T, hi = n * ((size_t) t + 1) / (size_t) T;
+				memcpy(to + lo, from + lo, hi - lo);
+			});
+			CQ_CUDA(cudaMemcpyAsync((uint8_t *) dst + off, to, n, cudaMemcpyHostToDevice, st));
+			CQ_CUDA(cudaEventRecord(ev[b], st));
+		}
+		return CQ_OK;
+	}
+};
+
 template <typename T>
-static int uploadArray(T **dst, const T *src, size_t n, cudaStream_t st) {
+static int uploadArray(T **dst, const T *src, size_t n, Uploader &up) {
 	size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
 	CQ_CUDA(cudaMalloc((void **) dst, bytes));
 	if (n > 0)
-		CQ_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+		return up.copy(*dst, src, n * sizeof(T));
 	return CQ_OK;
 }
 
@@ -366,14 +413,18 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaSetDevice(c->device));
 	freeDevice(c);
 	int rc;
-	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), c->stream)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), c->stream)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), c->stream)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), c->stream)) != 0) return rc;
-	std::vector<uint2> dref(f.d.numLeaves());
-	for (size_t i = 0; i < dref.size(); i++)
-		dref[i] = make_uint2(f.d.ref_id1[i], f.d.ref_id2[i]);
-	if ((rc = uploadArray(&c->d_leaf_d_ref, dref.data(), dref.size(), c->stream)) != 0) return rc;
+	Uploader up(c->stream);
+	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), up)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), up)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), up)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), up)) != 0) return rc;
+	FlatVec<uint2>::type dref(f.d.numLeaves());
+	up.pool.run([&](int t) {
+		const size_t T = (size_t) up.pool.size(), lo = dref.size() * (size_t) t / T, hi = dref.size() * ((size_t) t + 1) / T;
+		for (size_t i = lo; i < hi; i++)
+			dref[i] = make_uint2(f.d.ref_id1[i], f.d.ref_id2[i]);
+	});
+	if ((rc = uploadArray(&c->d_leaf_d_ref, dref.data(), dref.size(), up)) != 0) return rc;
 	CQ_CUDA(cudaStreamSynchronize(c->stream));
 
 	c->h = f.hash_len;
@@ -388,7 +439,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 4 * sizeof(unsigned long long)));
 
 	if (!f.filter.empty()) {
-		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), c->stream)) != 0) return rc;
+		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), up)) != 0) return rc;
 		c->filter_words = f.filter_words;
 		CQ_CUDA(cudaStreamSynchronize(c->stream));
 	}

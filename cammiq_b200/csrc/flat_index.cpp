@@ -118,20 +118,23 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 		for (unsigned p = 0; p < T; p++)
 			pool.emplace_back([&, p]() {
 				const uint64_t hi = nb * (p + 1) / T;
+				uint64_t fresh = 0;
+				// table accesses are cache misses: the home bucket of a key is prefetched kAhead
+				// owned keys before it is inserted
+				static const unsigned kAhead = 24;
+				struct Pending { uint64_t i, b; };
+				Pending ring[kAhead];
 				for (int t = 0; t < 2; t++) {
 					const DecodedIndex &x = t == 0 ? u : d;
 					const std::vector<uint8_t> &own = owner[t];
-					for (size_t i = 0; i < x.bucket_key.size(); i++) {
-						if (own[i] != (uint8_t) p)
-							continue;
-						const uint64_t key = x.bucket_key[i];
-						uint64_t b = homeBucketHost(key, u.hash_len, mask);
+					auto insert = [&](const Pending &e) {
+						const uint64_t key = x.bucket_key[e.i];
 						if (key >= key_limit) {
 							bad_key = true;
-							continue;
+							return;
 						}
 						TableSlot *hit = NULL;
-						for (; b < hi && hit == NULL; b++) {
+						for (uint64_t b = e.b; b < hi && hit == NULL; b++) {
 							TableSlot *s = &out.table[b * kSlotsPerBucket];
 							for (int k = 0; k < kSlotsPerBucket; k++) {
 								if (s[k].key == key) {
@@ -140,25 +143,39 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 								}
 								if (s[k].key == kEmptyKey) {
 									s[k].key = key;
-									fresh_keys[p]++;
+									fresh++;
 									hit = &s[k];
 									break;
 								}
 							}
 						}
 						if (hit == NULL) {
-							Deferred df = {(uint8_t) t, (uint64_t) i};
+							Deferred df = {(uint8_t) t, e.i};
 							deferred[p].push_back(df);
-							continue;
+							return;
 						}
 						// a repeated key inside one file: the later bucket replaces the earlier one, as
 						// map64[bucket] = root does (hashtrie.cpp:500)
 						if (t == 0)
-							hit->u_ref = x.bucket_root[i];
+							hit->u_ref = x.bucket_root[e.i];
 						else
-							hit->d_ref = x.bucket_root[i];
+							hit->d_ref = x.bucket_root[e.i];
+					};
+					uint64_t queued = 0;
+					for (size_t i = 0; i < x.bucket_key.size(); i++) {
+						if (own[i] != (uint8_t) p)
+							continue;
+						Pending e = {(uint64_t) i, homeBucketHost(x.bucket_key[i], u.hash_len, mask)};
+						__builtin_prefetch(&out.table[e.b * kSlotsPerBucket], 1);
+						if (queued >= kAhead)
+							insert(ring[queued % kAhead]); // the oldest entry: file order is kept
+						ring[queued % kAhead] = e;
+						queued++;
 					}
+					for (uint64_t q = queued > kAhead ? queued - kAhead : 0; q < queued; q++)
+						insert(ring[q % kAhead]);
 				}
+				fresh_keys[p] = fresh;
 			});
 		for (auto &th : pool) th.join();
 	}

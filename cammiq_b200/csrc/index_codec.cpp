@@ -30,17 +30,39 @@ int baseCode(uint8_t c) {
 namespace {
 
 // MSB-first bit cursor over the AUX stream; reads past the end return 1 (the reference
-// reader yields all-ones there, binaryio.cpp:146-149).
+// reader yields all-ones there, binaryio.cpp:146-149).  A 64-bit window holds the next bits
+// left-aligned and is refilled eight bytes at a time.
 struct BitCursor {
 	const uint8_t *p;
-	uint64_t nbits, pos;
-	inline uint32_t bit() {
-		if (pos >= nbits) {
-			pos++;
-			return 1;
+	uint64_t nbits, pos; // pos = stream position of the window's first bit
+	uint64_t win = 0;
+	uint32_t have = 0;   // valid bits in win
+	BitCursor(const uint8_t *data, uint64_t n_bits, uint64_t at) : p(data), nbits(n_bits), pos(at) {}
+	inline void refill() {
+		const uint64_t byte = pos >> 3, nbytes = (nbits + 7) >> 3;
+		uint64_t v;
+		if (byte + 8 <= nbytes) {
+			memcpy(&v, p + byte, 8);
+			v = __builtin_bswap64(v);
+		} else {
+			v = 0;
+			for (uint64_t i = 0; i < 8; i++)
+				v = (v << 8) | (byte + i < nbytes ? p[byte + i] : 0xFFu);
 		}
-		uint32_t v = (p[pos >> 3] >> (7 - (pos & 7))) & 1u;
-		pos++;
+		const uint32_t skip = (uint32_t) (pos & 7);
+		win = skip ? (v << skip) | ((1ull << skip) - 1) : v; // the vacated low bits are never consumed
+		have = 64 - skip;
+	}
+	inline void skip(uint32_t n) {
+		win <<= n;
+		have -= n;
+		pos += n;
+	}
+	inline uint32_t bit() {
+		if (have < 1)
+			refill();
+		const uint32_t v = (uint32_t) (win >> 63);
+		skip(1);
 		return v;
 	}
 	inline uint32_t bits(int n) {
@@ -49,13 +71,12 @@ struct BitCursor {
 			v = (v << 1) | bit();
 		return v;
 	}
-	// next five bits without consuming; 0b10000 is a leaf
+	// next five bits without consuming; 0b10000 is a leaf (padding past the end is all ones, so
+	// a truncated pattern can never read as one)
 	inline uint32_t peek5() {
-		if (pos + 5 > nbits)
-			return 0xFFu;
-		uint64_t byte = pos >> 3;
-		uint32_t w = ((uint32_t) p[byte] << 8) | (byte + 1 < ((nbits + 7) >> 3) ? p[byte + 1] : 0xFFu);
-		return (w >> (11 - (pos & 7))) & 0x1Fu;
+		if (have < 5)
+			refill();
+		return (uint32_t) (win >> 59);
 	}
 };
 
@@ -173,7 +194,7 @@ inline bool walkBucket(BitCursor &bc, Sink &sk, std::vector<Frame> &stack, uint3
 	root = kRefNone;
 	// fast path: the bucket is one leaf at depth h ("10000")
 	if (bc.peek5() == 0x10u) {
-		bc.pos += 5;
+		bc.skip(5);
 		root = sk.leaf(0);
 		return true;
 	}
@@ -187,7 +208,7 @@ inline bool walkBucket(BitCursor &bc, Sink &sk, std::vector<Frame> &stack, uint3
 		if (f.next < 4) {
 			uint8_t slot = f.next++;
 			if (bc.peek5() == 0x10u) {
-				bc.pos += 5;
+				bc.skip(5);
 				f.any = true;
 				sk.setChild(f.node, slot, sk.leaf((uint8_t) (f.depth + 1)));
 			} else if (bc.bit() != 0) {
@@ -251,7 +272,7 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 		err = "Cannot open file: " + path + ".aux.";
 		return CQ_EIO;
 	}
-	BitCursor bc = {aux.p, aux.n * 8, 0};
+	BitCursor bc(aux.p, aux.n * 8, 0);
 	out = DecodedIndex();
 	out.doubly_unique = bc.bit() != 0;
 	uint32_t option = bc.bits(7);
@@ -321,7 +342,7 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 			const size_t c = next.fetch_add(1);
 			if (c >= cps.size())
 				break;
-			BitCursor b2 = {aux.p, aux.n * 8, cps[c].aux_pos};
+			BitCursor b2(aux.p, aux.n * 8, cps[c].aux_pos);
 			StoreSink sk;
 			sk.out = &out;
 			sk.ints = ints.p;

@@ -7,6 +7,8 @@
 #define CAMMIQ_INDEX_CODEC_HPP
 
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -22,18 +24,33 @@ inline bool refIsLeaf(uint32_t r) { return (r & kRefLeafTag) != 0; }
 inline uint32_t refLeafId(uint32_t r) { return r & ~kRefLeafTag; }
 inline uint32_t refNodeId(uint32_t r) { return r - 1; }
 
+// std::vector whose resize() leaves new elements uninitialised: the decoder sizes its arrays
+// once and lets the worker threads that fill them take the page faults.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+	template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+	NoInitAlloc() {}
+	template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+	template <class U> void construct(U *p) { ::new ((void *) p) U; }
+	template <class U, class A> void construct(U *p, const A &a) { ::new ((void *) p) U(a); }
+};
+template <class T>
+struct FlatVec {
+	typedef std::vector<T, NoInitAlloc<T> > type;
+};
+
 struct DecodedIndex {
 	bool doubly_unique = false;
 	uint32_t hash_len = 0;
 	// buckets in file order
-	std::vector<uint64_t> bucket_key;
-	std::vector<uint32_t> bucket_root;
+	FlatVec<uint64_t>::type bucket_key;
+	FlatVec<uint32_t>::type bucket_root;
 	// internal trie nodes, 4 child refs each
-	std::vector<uint32_t> nodes;
+	FlatVec<uint32_t>::type nodes;
 	// leaves in file order
-	std::vector<uint32_t> ref_id1, ref_id2;
-	std::vector<uint16_t> ucount1, ucount2;
-	std::vector<uint8_t> depth;
+	FlatVec<uint32_t>::type ref_id1, ref_id2;
+	FlatVec<uint16_t>::type ucount1, ucount2;
+	FlatVec<uint8_t>::type depth;
 	uint32_t max_ref_id = 0;
 
 	uint64_t numLeaves() const { return ref_id1.size(); }
