@@ -413,8 +413,18 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaSetDevice(c->device));
 	freeDevice(c);
 	int rc;
+	const bool verbose = getenv("CAMMIQ_VERBOSE") != NULL;
+	auto t0 = std::chrono::high_resolution_clock::now();
+	auto lap = [&](const char *what) {
+		if (!verbose) return;
+		cudaStreamSynchronize(c->stream);
+		auto t1 = std::chrono::high_resolution_clock::now();
+		fprintf(stderr, "[upload] %s %.0f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	};
 	Uploader up(c->stream);
 	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), up)) != 0) return rc;
+	lap("prefix table");
 	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), up)) != 0) return rc;
 	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), up)) != 0) return rc;
 	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), up)) != 0) return rc;
@@ -426,6 +436,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	});
 	if ((rc = uploadArray(&c->d_leaf_d_ref, dref.data(), dref.size(), up)) != 0) return rc;
 	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	lap("tries and leaf records");
 
 	c->h = f.hash_len;
 	c->n_genomes = n_genomes;
@@ -452,6 +463,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 		CQ_CUDA(cudaMalloc((void **) &c->d_partials, (size_t) c->max_grid * ncnt * sizeof(uint32_t)));
 	CQ_CUDA(cudaMalloc((void **) &c->d_spill, (size_t) c->max_grid * kWarpsPerBlock * 32 * kHitSpill * sizeof(uint32_t)));
 	c->has_index = true;
+	lap("filter, counters, scratch");
 	return cq_reset(c);
 }
 

@@ -136,17 +136,8 @@ struct FileView {
 
 // The trie shape of one bucket is a pre-order bit string: '0' = no child, '1' + four children =
 // a node, and a node whose four children are all absent is a leaf (hashtrie.cpp:432-457).  The
-// walker below is shared by the two passes of the decoder through a sink:
-//   CountSink   pass 1, one thread: how many leaves / internal nodes precede every bucket
-//   StoreSink   pass 2, all threads: fills the flat arrays of a bucket range
-struct CountSink {
-	uint64_t leaves = 0, nodes = 0;
-	inline uint32_t newNode() { return (uint32_t) nodes++; }
-	inline void dropLastNode() { nodes--; }
-	inline uint32_t leaf(uint8_t) { return kRefLeafTag | (uint32_t) leaves++; }
-	inline void setChild(uint32_t, uint8_t, uint32_t) {}
-};
-
+// walker below fills the flat arrays of a bucket range through StoreSink (pass 2, all threads);
+// pass 1 only counts (scanBucketShape).
 struct StoreSink {
 	DecodedIndex *out;
 	const uint8_t *ints; // INT stream
@@ -243,6 +234,46 @@ inline bool walkBucket(BitCursor &bc, Sink &sk, std::vector<Frame> &stack, uint3
 	return true;
 }
 
+// Pass 1 needs counts only, and a leaf is recognisable where it starts ('1' followed by four
+// absent children), so the shape of a bucket can be scanned without a stack: `pending` child
+// slots remain to be read; an absent child uses one up, a leaf uses one up, an internal node
+// uses one up and opens four.  Internal nodes are counted in pre-order, which is the order the
+// fill pass numbers them in.
+inline bool scanBucketShape(BitCursor &bc, uint64_t &leaves, uint64_t &nodes) {
+	uint32_t v = bc.peek5();
+	if (v == 0x10u) {
+		bc.skip(5);
+		leaves++;
+		return true;
+	}
+	bc.skip(1);
+	if (!(v & 0x10u))
+		return true; // no trie under this bucket
+	nodes++;
+	uint64_t pending = 4;
+	while (pending > 0) {
+		v = bc.peek5();
+		if (!(v & 0x10u)) {
+			// a run of absent children (up to the five bits in view)
+			const uint64_t zeros = (uint64_t) __builtin_clz((v << 27) | (1u << 26));
+			const uint64_t n = zeros < pending ? zeros : pending;
+			bc.skip((uint32_t) n);
+			pending -= n;
+		} else if (v == 0x10u) {
+			bc.skip(5);
+			leaves++;
+			pending--;
+		} else {
+			bc.skip(1);
+			nodes++;
+			pending += 3;
+			if (pending > 3 * 4096 || bc.pos > bc.nbits + 64)
+				return false;
+		}
+	}
+	return true;
+}
+
 struct Checkpoint {
 	uint64_t aux_pos, leaves, nodes;
 };
@@ -289,11 +320,30 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 	const uint32_t h = out.hash_len, leaf_bytes = dd ? 12 : 6;
 
 	auto t_start = std::chrono::high_resolution_clock::now();
+	// the shape pass is one thread walking both mapped files front to back; without this it
+	// would also take every page fault of the mappings by itself
+	{
+		const unsigned Tp = decodeThreads();
+		std::vector<std::thread> pool;
+		std::atomic<uint64_t> sink(0);
+		for (unsigned t = 0; t < Tp; t++)
+			pool.emplace_back([&, t]() {
+				uint64_t acc = 0;
+				const FileView *files[2] = {&ints, &aux};
+				for (int f = 0; f < 2; f++) {
+					const uint64_t n = files[f]->n, lo = n / Tp * t, hi = t + 1 == Tp ? n : n / Tp * (t + 1);
+					for (uint64_t i = lo; i < hi; i += 4096)
+						acc += files[f]->p[i];
+				}
+				sink += acc;
+			});
+		for (auto &th : pool) th.join();
+	}
+	auto t_touch = std::chrono::high_resolution_clock::now();
 	// ---- pass 1: shape only
 	std::vector<Checkpoint> cps;
 	cps.reserve((size_t) (ints.n / (8 + leaf_bytes) / kCheckpointBuckets + 2));
-	CountSink cs;
-	std::vector<Frame> stack;
+	struct { uint64_t leaves, nodes; } cs = {0, 0};
 	uint64_t buckets = 0;
 	for (;;) {
 		const uint64_t at = 8 * buckets + (uint64_t) leaf_bytes * cs.leaves;
@@ -309,8 +359,7 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 			Checkpoint c = {bc.pos, cs.leaves, cs.nodes};
 			cps.push_back(c);
 		}
-		uint32_t root;
-		if (!walkBucket(bc, cs, stack, root) || bc.pos > bc.nbits + 64) {
+		if (!scanBucketShape(bc, cs.leaves, cs.nodes) || bc.pos > bc.nbits + 64) {
 			err = "Index " + path + ": AUX stream is malformed (runaway trie).";
 			return CQ_EFORMAT;
 		}
@@ -378,8 +427,9 @@ int decodeIndexFile(const std::string &path, DecodedIndex &out, std::string &err
 		for (auto &th : pool) th.join();
 	}
 	if (getenv("CAMMIQ_VERBOSE"))
-		fprintf(stderr, "[decode] %s: %lu buckets, shape pass %.0f ms, fill pass %.0f ms on %u threads\n", path.c_str(),
-			(unsigned long) buckets, std::chrono::duration<double, std::milli>(t_pass1 - t_start).count(),
+		fprintf(stderr, "[decode] %s: %lu buckets, page-in %.0f ms, shape pass %.0f ms, fill pass %.0f ms on %u threads\n", path.c_str(),
+			(unsigned long) buckets, std::chrono::duration<double, std::milli>(t_touch - t_start).count(),
+			std::chrono::duration<double, std::milli>(t_pass1 - t_touch).count(),
 			std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t_pass1).count(), T);
 	if (broken) {
 		err = "Index " + path + ": AUX stream is malformed (runaway trie).";
