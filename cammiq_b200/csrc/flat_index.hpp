@@ -15,6 +15,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <sys/mman.h>
 #include <string>
 #include <vector>
 
@@ -131,10 +132,24 @@ struct RawArray {
 	~RawArray() { free(p); }
 	bool alloc(size_t count) {
 		free(p);
+		p = NULL;
 		n = 0;
-		p = (T *) malloc(sizeof(T) * (count ? count : 1));
-		if (p == NULL)
+		// 2 MB alignment + MADV_HUGEPAGE: a multi-GB table probed at random is TLB-bound with
+		// 4 KB pages, and first-touching it takes one fault per page
+		const size_t bytes = sizeof(T) * (count ? count : 1), huge = (size_t) 2 << 20;
+		void *q = NULL;
+		if (bytes >= 4 * huge) {
+			if (posix_memalign(&q, huge, (bytes + huge - 1) / huge * huge) != 0)
+				q = NULL;
+#ifdef MADV_HUGEPAGE
+			if (q != NULL)
+				madvise(q, (bytes + huge - 1) / huge * huge, MADV_HUGEPAGE);
+#endif
+		} else
+			q = malloc(bytes);
+		if (q == NULL)
 			return false;
+		p = (T *) q;
 		n = count;
 		return true;
 	}
