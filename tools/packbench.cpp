@@ -1,3 +1,6 @@
+// Host-side micro-benchmark of the 2-bit read packer (cammiq_b200/csrc/pack_reads.cpp): thread
+// scaling of packBatch against a pure streaming pass over the same bytes.  Build and run:
+//   g++ -O3 -std=c++11 -pthread -Icammiq_b200/csrc tools/packbench.cpp cammiq_b200/csrc/pack_reads.cpp -o /tmp/packbench && /tmp/packbench
 #include "pack_reads.hpp"
 #include <chrono>
 #include <cstdio>

@@ -1,3 +1,5 @@
+"""Index load / GPU context / upload wall times on the GPU box (cfg2 index); CAMMIQ_VERBOSE=1 adds
+the per-phase lines of the decoder, the table build and the upload."""
 import sys, time, os
 sys.path.insert(0, "/root/repo")
 import cammiq_b200 as cq
