@@ -251,9 +251,34 @@ __device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, boo
 	return strand ? reverseGroups(~hv) >> (64 - 2 * n) : hv;
 }
 
+// Leaves under a bucket root reached by one strand of a read go to the read's hit list.
+template <bool PACKED>
+__device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws, uint32_t *warp_spill, const uint8_t *s,
+		uint32_t slot, uint32_t rl, uint32_t strand, uint32_t next, unsigned long long refs, uint32_t &n_leaf_hits) {
+	uint32_t leaf[2];
+	leaf[0] = descend<PACKED>((uint32_t) refs, p.nodes_u, s, rl, strand, next);
+	leaf[1] = descend<PACKED>((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, next);
+#pragma unroll
+	for (int t = 0; t < 2; t++) {
+		if (leaf[t] == kRefNone)
+			continue;
+		n_leaf_hits++;
+		uint32_t e = (leaf[t] & ~kRefLeafTag) | (t ? kRefLeafTag : 0u);
+		// 16-bit shared counter bumped through its containing 32-bit word
+		uint32_t *word = reinterpret_cast<uint32_t *>(&ws.hit_cnt[slot & ~1u]);
+		uint32_t old = atomicAdd(word, (slot & 1u) ? 0x10000u : 1u);
+		uint32_t at = (slot & 1u) ? (old >> 16) : (old & 0xFFFFu);
+		if (at < (uint32_t) kHitSeg) ws.hits[slot][at] = e;
+		else if (at < (uint32_t) (kHitSeg + kHitSpill)) warp_spill[(size_t) slot * kHitSpill + at - kHitSeg] = e;
+	}
+}
+
 // Phase 2: the warp drains its candidate queue.  One candidate per lane: recompute the h-mer,
 // probe the prefix table (HBM), descend, append leaves to the owning read's hit list.
-template <bool PACKED>
+// FILTER: phase 1 does not look for palindromic h-mers (equal to their own reverse complement);
+// for those the forward candidate also serves the reverse strand here and a reverse candidate
+// (a false positive of the filter's other pattern) is dropped.
+template <bool PACKED, bool FILTER>
 __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, const uint8_t *buf, uint32_t *warp_spill,
 		int lane, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
@@ -269,6 +294,9 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 			const unsigned long long hv = strandWindow<PACKED>(s, ws.staged != 0, rl, strand, pos, h);
 			// keys are placed by their canonical h-mer (flat_index.hpp, homeBucketHost)
 			const unsigned long long hv_rc = reverseGroups(~hv) >> (64 - 2 * h);
+			const bool palin = FILTER && hv == hv_rc;
+			if (palin && strand)
+				continue;
 			uint64_t b = mixKey(hv < hv_rc ? hv : hv_rc) & p.table_mask;
 			unsigned long long k0, r0, k1, r1, refs = 0;
 			bool found = false;
@@ -282,22 +310,9 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, c
 				n_chained++;
 			}
 			if (found) {
-				uint32_t leaf[2];
-				leaf[0] = descend<PACKED>((uint32_t) refs, p.nodes_u, s, rl, strand, pos + h);
-				leaf[1] = descend<PACKED>((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, pos + h);
-#pragma unroll
-				for (int t = 0; t < 2; t++) {
-					if (leaf[t] == kRefNone)
-						continue;
-					n_leaf_hits++;
-					uint32_t e = (leaf[t] & ~kRefLeafTag) | (t ? kRefLeafTag : 0u);
-					// 16-bit shared counter bumped through its containing 32-bit word
-					uint32_t *word = reinterpret_cast<uint32_t *>(&ws.hit_cnt[slot & ~1u]);
-					uint32_t old = atomicAdd(word, (slot & 1u) ? 0x10000u : 1u);
-					uint32_t at = (slot & 1u) ? (old >> 16) : (old & 0xFFFFu);
-					if (at < (uint32_t) kHitSeg) ws.hits[slot][at] = e;
-					else if (at < (uint32_t) (kHitSeg + kHitSpill)) warp_spill[(size_t) slot * kHitSpill + at - kHitSeg] = e;
-				}
+				collectLeaves<PACKED>(p, ws, warp_spill, s, slot, rl, strand, pos + h, refs, n_leaf_hits);
+				if (palin) // the reverse strand holds the same h-mer at position rl-h-pos
+					collectLeaves<PACKED>(p, ws, warp_spill, s, slot, rl, 1u, rl - pos, refs, n_leaf_hits);
 			}
 		}
 	}
@@ -475,9 +490,10 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 						// hr is the reverse complement of the window hf covers: ONE probe with the
 						// canonical h-mer answers both strands
 						uint32_t a;
-						filterHash(hf < hr ? hf : hr, a, bsel[u]);
-						// the two lowest bits of B are unused by the selectors: remember the orientation
-						bsel[u] = (bsel[u] & ~3u) | (hf <= hr ? 1u : 0u) | (hf == hr ? 2u : 0u);
+						const bool fwd_is_canon = hf <= hr;
+						filterHash(fwd_is_canon ? hf : hr, a, bsel[u]);
+						// the lowest bit of B is unused by the selectors: remember the orientation
+						bsel[u] = (bsel[u] & ~1u) | (fwd_is_canon ? 1u : 0u);
 						ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
 					} else {
 						kf[u] = hf;
@@ -492,15 +508,16 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 					const uint32_t j = j0 + u;
 					bool cand_f = false, cand_r = false;
 					if (j + 1 >= h && j < rl) {
-						n_probes += 2;
 						if (FILTER) {
 							// pattern of B: the canonical orientation is a key; other pattern: its reverse
 							// complement is.  fwd_canon says which strand holds the canonical orientation.
 							const bool same = filterTest(ff[u].x, ff[u].y, bsel[u]);
 							const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
-							const bool fwd_canon = (bsel[u] & 1u) != 0, palin = (bsel[u] & 2u) != 0;
+							// (a palindromic h-mer is its own reverse complement: phase 2 serves its reverse
+							// strand from the forward candidate)
+							const bool fwd_canon = (bsel[u] & 1u) != 0;
 							cand_f = fwd_canon ? same : other;
-							cand_r = (fwd_canon && !palin) ? other : same;
+							cand_r = fwd_canon ? other : same;
 						} else {
 							// candidate = the bucket holds the key, or is full and the key may have spilled
 							// the reverse strand's key is recomputed rather than kept live across the loads
@@ -510,27 +527,31 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							cand_r = bk[u][0] == kr || bk[u][2] == kr || full;
 						}
 					}
-					if (cand_f) {
-						// forward strand, position i = j-h+1
-						uint32_t at = atomicAdd(&ws.q_count, 1u);
-						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
-						n_cand++;
-					}
-					if (cand_r) {
-						// reverse-complement strand: this window is rc position rl-1-j
-						uint32_t at = atomicAdd(&ws.q_count, 1u);
-						ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
-						n_cand++;
+					if (cand_f | cand_r) { // rare: one branch on the common path
+						if (cand_f) {
+							// forward strand, position i = j-h+1
+							uint32_t at = atomicAdd(&ws.q_count, 1u);
+							ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
+							n_cand++;
+						}
+						if (cand_r) {
+							// reverse-complement strand: this window is rc position rl-1-j
+							uint32_t at = atomicAdd(&ws.q_count, 1u);
+							ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
+							n_cand++;
+						}
 					}
 				}
 				__syncwarp();
 				// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
 				if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
-					drainQueue<PACKED>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+					drainQueue<PACKED, FILTER>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 			}
 		}
 		const bool bad = bad4 != 0;
-		drainQueue<PACKED>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+		if (have && rl >= h)
+			n_probes += 2 * (rl - h + 1); // both strands of every window
+		drainQueue<PACKED, FILTER>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
 
 		// ---- phase 3: thread per read: leaf set -> decision (query.cpp:529-636) ------------------
 		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;

@@ -99,6 +99,25 @@ def test_extreme_hash_lengths(ctx, tmp_path, h):
     assert (want["read_class"] >= 2).sum() > 0
 
 
+@pytest.mark.parametrize("h", [6, 8])
+def test_palindromic_hmers(ctx, tmp_path, h):
+    """An h-mer equal to its own reverse complement (even h only) is found by BOTH strands of a
+    window; phase 1 keeps no flag for it, phase 2 serves the reverse strand from the forward
+    candidate.  The sequence is seeded with palindromes so that many keys are palindromic."""
+    rng = np.random.default_rng(600 + h)
+    parts = []
+    for _ in range(250):
+        half = random_seq(rng, h // 2)
+        parts.append(half + half.translate(COMP)[::-1])          # a palindromic h-mer
+        parts.append(random_seq(rng, int(rng.integers(3, 9))))
+    seq = b"".join(parts)
+    pu, pd = build_case(tmp_path, h, 5, seq, stride=1, deep=3, tag="pal%d" % h)
+    reads = sample_reads(rng, seq, 400, h, 200, err=0.0)
+    reads += [p for p in parts[0:40:2]]                           # the palindromes alone
+    want = compare(ctx, pu, pd, 5, reads, leaf_cap=600)
+    assert (want["read_nleaf_u"] + want["read_nleaf_d"]).max() > 4
+
+
 def test_more_genomes_than_shared_counters(ctx, tmp_path):
     """G = 9000 > 8191: genome counters fall back to global 64-bit atomics."""
     rng = np.random.default_rng(7)
