@@ -14,6 +14,8 @@
  *   cq_index_upload                   end of loadIdx_p (index becomes resident)
  *   cq_query                          FqReader::query64_p / query64mt_p (CQ_MODE_P)
  *                                     FqReader::query64_sc (CQ_MODE_SC)       query.cpp:458-1080
+ *   cq_query_packed / cq_pack_reads   the read storage readFastq fills        query.cpp:371-425
+ *   cq_ctx_set_host_packing           (ASCII `reads` vector -> 2-bit codes before PCIe)
  *   cq_reset                          resetCounters / resetCounters_sc        query.cpp:1820-1858
  *   cq_get_timing                     the "Time for query" bracket            query.cpp:645-647
  *
