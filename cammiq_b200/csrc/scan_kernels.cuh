@@ -1,13 +1,14 @@
 // sm_100a kernels of the read-matching path.
 //
-//   scan_reads_kernel      A1-A8 in one launch: a CTA pulls a tile of 256 ASCII reads into
-//                          shared memory with one TMA bulk copy (cp.async.bulk + mbarrier),
-//                          then
+//   scan_reads_kernel      A1-A8 in one launch, persistent grid: every WARP pulls sub-tiles of
+//                          32 reads (ASCII, or 2-bit packed by the host) into its own shared-
+//                          memory buffer with one TMA bulk copy (cp.async.bulk + mbarrier), then
 //                            phase 1 (thread per read): decode each base to its 2-bit code,
 //                              roll the h-base prefix hash of BOTH strands in registers and
-//                              test every position against the L2-resident membership filter
-//                              (or the prefix table itself when the index is too large for a
-//                              filter); positives go to a per-warp queue,
+//                              test the canonical h-mer of every position against the L2-
+//                              resident membership filter (or the prefix table itself when the
+//                              index is too large for a filter); positives go to a per-warp
+//                              queue,
 //                            phase 2 (warp-cooperative): queued candidates probe the prefix
 //                              table in HBM (one 32-byte sector = one bucket) and descend the
 //                              CSR trie; leaves land in per-read hit lists,
