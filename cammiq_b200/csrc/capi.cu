@@ -103,6 +103,8 @@ struct cq_ctx {
 	// SC pair records (device, grows)
 	unsigned long long *d_pairs = NULL;
 	size_t cap_pairs = 0;
+	PairSlot *d_pair_table = NULL, *d_pair_out = NULL; // aggregation scratch of cq_fetch
+	size_t cap_pair_table = 0, cap_pair_out = 0;
 	// per-read outputs (device, sized per call)
 	uint8_t *d_read_class = NULL;
 	uint32_t *d_read_rid_a = NULL, *d_read_rid_b = NULL, *d_nleaf_u = NULL, *d_nleaf_d = NULL,
@@ -324,7 +326,7 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	freeDevice(c);
 	cudaFree(c->d_bases); cudaFree(c->d_offsets); cudaFree(c->d_lengths);
-	cudaFree(c->d_pairs); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
+	cudaFree(c->d_pairs); cudaFree(c->d_pair_table); cudaFree(c->d_pair_out); cudaFree(c->d_read_class); cudaFree(c->d_read_rid_a);
 	cudaFree(c->d_read_rid_b); cudaFree(c->d_nleaf_u); cudaFree(c->d_nleaf_d); cudaFree(c->d_leaf_u);
 	cudaFree(c->d_leaf_d);
 	for (int i = 0; i < 2; i++)
@@ -770,24 +772,36 @@ extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
 	out->n_invalid = counts[ncnt + 2];
 	out->n_pairs = 0;
 	if (mode == CQ_MODE_SC) {
-		// read_cnts_b (query.cpp:994-997): aggregate the per-read pair records on the host
-		uint64_t nrec = counts[ncnt + 3];
-		std::vector<unsigned long long> rec(nrec);
+		// read_cnts_b (query.cpp:994-997): the per-read pair records are folded into (pair, count)
+		// entries on the device; only the distinct pairs come back and are put in (a, b) order here
+		const uint64_t nrec = counts[ncnt + 3];
+		std::vector<PairSlot> agg;
 		if (nrec > 0) {
-			CQ_CUDA(cudaMemcpy(rec.data(), c->d_pairs, nrec * 8, cudaMemcpyDeviceToHost));
-			std::sort(rec.begin(), rec.end());
+			uint64_t slots = 1024;
+			while (slots < 2 * nrec)
+				slots <<= 1;
+			int rc;
+			if ((rc = ensure(&c->d_pair_table, &c->cap_pair_table, (size_t) slots)) != 0) return rc;
+			if ((rc = ensure(&c->d_pair_out, &c->cap_pair_out, (size_t) nrec + 1)) != 0) return rc;
+			init_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots);
+			aggregate_pairs_kernel<<<(unsigned) ((nrec + 255) / 256), 256, 0, c->stream>>>(c->d_pairs, nrec, c->d_pair_table, slots - 1);
+			unsigned long long *d_n = reinterpret_cast<unsigned long long *>(c->d_pair_out + nrec);
+			CQ_CUDA(cudaMemsetAsync(d_n, 0, sizeof(PairSlot), c->stream));
+			compact_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots, c->d_pair_out, d_n);
+			c->timing.kernel_launches += 3;
+			unsigned long long n_distinct = 0;
+			CQ_CUDA(cudaMemcpyAsync(&n_distinct, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+			CQ_CUDA(cudaStreamSynchronize(c->stream));
+			agg.resize((size_t) n_distinct);
+			if (n_distinct > 0)
+				CQ_CUDA(cudaMemcpy(agg.data(), c->d_pair_out, (size_t) n_distinct * sizeof(PairSlot), cudaMemcpyDeviceToHost));
+			std::sort(agg.begin(), agg.end(), [](const PairSlot &x, const PairSlot &y) { return x.key < y.key; });
 		}
-		uint64_t np = 0;
-		for (uint64_t i = 0; i < nrec;) {
-			uint64_t j = i;
-			while (j < nrec && rec[j] == rec[i]) j++;
-			if (out->pairs && np < out->pairs_cap) {
-				out->pairs[np].a = (uint32_t) (rec[i] >> 32);
-				out->pairs[np].b = (uint32_t) rec[i];
-				out->pairs[np].count = j - i;
-			}
-			np++;
-			i = j;
+		const uint64_t np = agg.size();
+		for (uint64_t i = 0; i < np && out->pairs && i < out->pairs_cap; i++) {
+			out->pairs[i].a = (uint32_t) (agg[i].key >> 32);
+			out->pairs[i].b = (uint32_t) agg[i].key;
+			out->pairs[i].count = agg[i].count;
 		}
 		out->n_pairs = np;
 		if (out->pairs && np > out->pairs_cap)

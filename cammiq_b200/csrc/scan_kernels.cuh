@@ -14,6 +14,8 @@
 //                              CSR trie; leaves land in per-read hit lists,
 //                            phase 3 (thread per read): leaf set -> decision -> counters.
 //   reduce_partials_kernel per-block genome-count partials -> 64-bit totals (no atomics)
+//   init_pairs_kernel, aggregate_pairs_kernel, compact_pairs_kernel
+//                          query64_sc's pair map: per-read pair records -> (pair, count) entries
 //   random_*_kernel        measured lookup roofline (random gathers from L2 / HBM)
 //
 // Reference behaviour reproduced: query.cpp:480-527 (scan of every position, both strands),
@@ -715,6 +717,55 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const uint32_t *__
 	for (uint32_t b = 0; b < n_blocks; b++)
 		sum += partials[(size_t) b * ncnt + i];
 	counts[i] += sum;
+}
+
+// read_cnts_b of query64_sc (query.cpp:994-997): the scan leaves one (a<<32|b) record per
+// D_PAIR read; these two kernels fold them into (pair, count) entries on the device so that
+// only the distinct pairs cross PCIe.  Open-addressing table, capacity a power of two >= 2x
+// the number of records (cannot fill up); lanes of a warp holding the same pair combine first,
+// so a sample dominated by one pair does not serialise on one address.
+struct PairSlot {
+	unsigned long long key;   // a<<32 | b, kEmptyKey = free
+	unsigned long long count;
+};
+
+__global__ void __launch_bounds__(256) init_pairs_kernel(PairSlot *table, uint64_t n_slots) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_slots) {
+		table[i].key = kEmptyKey;
+		table[i].count = 0;
+	}
+}
+
+__global__ void __launch_bounds__(256) aggregate_pairs_kernel(const unsigned long long *__restrict__ records, uint64_t n_records,
+		PairSlot *table, uint64_t mask) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const bool have = i < n_records;
+	const unsigned long long key = have ? records[i] : kEmptyKey;
+	const unsigned active = __ballot_sync(0xffffffffu, have);
+	if (!have)
+		return;
+	const unsigned peers = __match_any_sync(active, key);
+	if ((int) (threadIdx.x & 31u) != __ffs(peers) - 1)
+		return; // another lane of the warp adds for this pair
+	const unsigned long long add = (unsigned long long) __popc(peers);
+	uint64_t b = mixKey(key) & mask;
+	for (;;) {
+		const unsigned long long seen = atomicCAS(&table[b].key, kEmptyKey, key);
+		if (seen == kEmptyKey || seen == key) {
+			atomicAdd(&table[b].count, add);
+			return;
+		}
+		b = (b + 1) & mask;
+	}
+}
+
+__global__ void __launch_bounds__(256) compact_pairs_kernel(const PairSlot *__restrict__ table, uint64_t n_slots, PairSlot *out,
+		unsigned long long *n_out) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_slots || table[i].key == kEmptyKey)
+		return;
+	out[atomicAdd(n_out, 1ull)] = table[i];
 }
 
 // ------------------------------------------------------------------- lookup roofline probes
