@@ -421,6 +421,15 @@ def run(json_fd):
         if pk_s < ascii_s:
             e2e_s, h2d, e2e_path = pk_s, int(tm_pk["h2d_bytes"]), "host_packed_2bit"
     e2e_value = world * n / e2e_s
+    # the chunked host path must leave exactly the counters of the single resident launch
+    if world == 1:
+        same = (int(res["nundet"]), int(res["nconf"]), int(res["cnt_u"].sum()), int(res["cnt_d"].sum())) == (
+            int(mine["nundet"]), int(mine["nconf"]), int(mine["cnt_u"].sum()), int(mine["cnt_d"].sum()))
+        if mode == cq.MODE_P:
+            same = same and np.array_equal(res["rcount_u"], mine["rcount_u"]) and np.array_equal(res["rcount_d"], mine["rcount_d"])
+        e2e_check = "ok" if same else "MISMATCH"
+    else:
+        e2e_check = None
     d2h = (2 * (w["n_genomes"] + 1) + 4) * 8 + ((info.n_leaves_u + info.n_leaves_d) * 4 if mode == cq.MODE_P else 0)
     ctx.set_host_packing(-1)
 
@@ -479,6 +488,7 @@ def run(json_fd):
                          "frac_of_random_gather": (stats["probes"] / (scan_ms * 1e-3) / 1e9) / gsec if gsec else None},
             "cpu_baseline": cpu,
             "parity_vs_reference_sample": parity,
+            "e2e_equals_resident_launch": e2e_check,
             "multi_gpu_reduce_check": multi_check,
             "result": {"nundet": int(mine["nundet"]), "nconf": int(mine["nconf"]),
                        "sum_u": int(mine["cnt_u"].sum()), "sum_d": int(mine["cnt_d"].sum())},

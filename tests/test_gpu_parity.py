@@ -166,7 +166,8 @@ def test_dense_index_spills_hit_list(ctx, tmp_path):
 
 
 def test_chunked_pipeline_matches_single_launch_and_oracle(ctx, tmp_path):
-    """cq_query streams reads in 2^20-read chunks through two staging buffers; the result must
+    """cq_query streams reads in 2^20-read chunks through three rotating staging buffers (five
+    chunks here, so buffers are reused while earlier chunks are still in flight); the result must
     equal the single-launch device-resident path, and per-read records around the chunk
     boundaries must equal the oracle (fixed-stride and offsets addressing, ragged lengths)."""
     from cammiq_b200 import synthlib as sl
@@ -175,7 +176,7 @@ def test_chunked_pipeline_matches_single_launch_and_oracle(ctx, tmp_path):
     iu, idd = str(tmp_path / "index_u.bin1"), str(tmp_path / "index_d.bin2")
     idx = cq.Index(iu, idd)
     ctx.upload(idx, 12)
-    n, rl = (1 << 21) + 12345, 100
+    n, rl = (1 << 22) + 12345, 100
     reads = sl.make_reads(p, 0, n, rl, 0.01)
     rng = np.random.default_rng(1)
     lengths = rng.integers(60, rl + 1, size=n).astype(np.uint8)
@@ -205,7 +206,7 @@ def test_chunked_pipeline_matches_single_launch_and_oracle(ctx, tmp_path):
         assert np.array_equal(a[k], c2[k]), k
     # (c) oracle on windows around the chunk boundaries
     ou, od = ol.OracleIndex(iu), ol.OracleIndex(idd)
-    for lo in (0, (1 << 20) - 1500, (1 << 21) - 1500, n - 3000):
+    for lo in (0, (1 << 20) - 1500, (1 << 21) - 1500, 3 * (1 << 20) - 1500, (1 << 22) - 1500, n - 3000):
         hi = min(lo + 3000, n)
         want = ol.oracle_query(ou, od, ol.MODE_P, 12, flat, np.arange(lo, hi, dtype=np.uint64) * rl,
                                lengths[lo:hi], per_read=True)
