@@ -95,7 +95,7 @@ inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline uint32_t filterOtherPattern(uint32_t B) { return (B >> 12) * 0x2C1B3C6Du + 0x9E3779B9u; } // only the selector bits of B
+inline uint32_t filterOtherPattern(uint32_t B) { return B * 0x58367ADAu + 0x9E3779B9u; } // even multiplier: bit 31 of B (the scan's orientation flag) has no influence
 // word index for a filter of `words` words (any count below 2^32): the high half of A * words
 #if defined(__CUDACC__)
 __host__ __device__
@@ -107,17 +107,28 @@ inline uint32_t filterWordIndex(uint32_t A, uint32_t words) {
 	return (uint32_t) (((uint64_t) A * words) >> 32);
 #endif
 }
-// all four selected bits set in the word (x = low half, y = high half)?
+// B selects four bits of the 64-bit word as (byte, bit) pairs: byte indices = the four nibbles
+// of B & 0x7777, bits inside those bytes = the four nibbles of (B >> 16) & 0x7777.  On the device
+// that is two byte permutes: one gathers the four selected bytes of the word, one builds the four
+// one-bit masks from a constant table -- no variable shifts.
+inline uint64_t filterMask(uint32_t B) {
+	uint64_t m = 0;
+	for (int i = 0; i < 4; i++)
+		m |= 1ull << (8 * ((B >> (4 * i)) & 7u) + ((B >> (16 + 4 * i)) & 7u));
+	return m;
+}
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
 inline bool filterTest(uint32_t x, uint32_t y, uint32_t B) {
-	return ((x >> (B >> 27)) & (x >> ((B >> 22) & 31u)) & (y >> ((B >> 17) & 31u)) & (y >> ((B >> 12) & 31u)) & 1u) != 0;
-}
-inline uint64_t filterMask(uint32_t B) {
-	uint32_t lo = (1u << (B >> 27)) | (1u << ((B >> 22) & 31u));
-	uint32_t hi = (1u << ((B >> 17) & 31u)) | (1u << ((B >> 12) & 31u));
-	return (uint64_t) lo | ((uint64_t) hi << 32);
+#if defined(__CUDA_ARCH__)
+	const uint32_t bytes = __byte_perm(x, y, B & 0x7777u);
+	const uint32_t bits = __byte_perm(0x08040201u, 0x80402010u, (B >> 16) & 0x7777u);
+	return (~bytes & bits) == 0u;
+#else
+	const uint64_t m = filterMask(B), w = (uint64_t) x | ((uint64_t) y << 32);
+	return (w & m) == m;
+#endif
 }
 
 // Uninitialised, owning array (the multi-GB table is first-touched by the build threads

@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 						uint32_t a;
 						const bool fwd_is_canon = hf <= hr;
 						filterHash(fwd_is_canon ? hf : hr, a, bsel[u]);
-						// the lowest bit of B is unused by the selectors: remember the orientation
-						bsel[u] = (bsel[u] & ~1u) | (fwd_is_canon ? 1u : 0u);
+						// bit 31 of B is unused by the selectors: remember the orientation
+						bsel[u] = (bsel[u] & 0x7FFFFFFFu) | (fwd_is_canon ? 0x80000000u : 0u);
 						ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
 					} else {
 						kf[u] = hf;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 							const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
 							// (a palindromic h-mer is its own reverse complement: phase 2 serves its reverse
 							// strand from the forward candidate)
-							const bool fwd_canon = (bsel[u] & 1u) != 0;
+							const bool fwd_canon = (bsel[u] & 0x80000000u) != 0;
 							cand_f = fwd_canon ? same : other;
 							cand_r = fwd_canon ? other : same;
 						} else {
