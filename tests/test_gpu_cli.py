@@ -92,3 +92,31 @@ def test_cli_ilp_inputs_dump(tmp_path):
             assert int(r[2]) == l and int(r[8]) == int(rc[l])
             w1 = float(oi.ucount1[l]) * (rl - float(oi.depth[l])) / rl * (1.0 - float(np.float32(0.01))) ** float(oi.depth[l])
             assert abs(float(r[9]) - w1) <= 1e-9 * max(1.0, abs(w1))
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("case", ["cfg1_small", "adversarial_250"])
+def test_cli_two_gpus_equal_one(case, tmp_path):
+    """--gpus 2: packed reads sharded over two devices, counters combined (NCCL reduce in standard
+    mode, host merge of the pair maps with --read_cnts): same files as the single-GPU run."""
+    c = load_case(case)
+    base = ["--query", "-f", c["map"], "-q", c["fq"], "-i", c["iu"], c["id"]]
+    for extra, tag in ((["--read_cnts"], "sc"), (["-e", "0.01"], "p")):
+        outs = []
+        for g in ("1", "2"):
+            out, dump = str(tmp_path / ("%s_%s.out" % (tag, g))), str(tmp_path / ("%s_%s.tsv" % (tag, g)))
+            args = base[:1] + extra + base[1:] + ["-o", out, "--gpus", g]
+            if tag == "p":
+                args += ["--dump_ilp_inputs", dump]
+            err = run_cli(args)
+            outs.append((err, open(out, "rb").read() if os.path.exists(out) else b"",
+                         open(dump, "rb").read() if tag == "p" else b""))
+        assert outs[0] == outs[1], (case, tag)
