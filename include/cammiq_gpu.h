@@ -138,7 +138,11 @@ int cq_index_find_host(const cq_index *idx, int table, uint64_t bucket, const ui
 /* ------------------------------------------------------------------- device context -- */
 
 /* device = CUDA ordinal.  stream = a cudaStream_t the caller wants the work enqueued on
-   (e.g. torch's current stream), or NULL to let the context create its own. */
+   (e.g. torch's current stream), or NULL to let the context create its own.
+   A context is not thread-safe: use it from one thread at a time (one context per GPU, each
+   driven by its own thread or process, is the multi-GPU pattern).  A cq_index is immutable
+   after cq_index_load / cq_index_set_filter_budget and may be uploaded to any number of
+   contexts concurrently. */
 int cq_ctx_create(int device, void *stream, cq_ctx **out);
 void cq_ctx_destroy(cq_ctx *ctx);
 
