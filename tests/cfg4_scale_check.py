@@ -76,6 +76,9 @@ hit = np.where(single, ra == src, np.where(pair, (ra == src) | (rb == src), True
 out["assigned_reads_on_source_genome_frac"] = float(hit[single | pair].mean())
 out["class_histogram"] = {int(k): int(v) for k, v in zip(*np.unique(cls, return_counts=True))}
 json.dump(out, open("gpurun_out/cfg4_check.json", "w"), indent=1)
+if os.environ.get("CFG4_SKIP_ORACLE"):
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 # oracle on a sample (test infrastructure; loads both tries on the host)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 import oracle_lib as ol  # noqa: E402
