@@ -8,8 +8,8 @@ raises.
 """
 from .capi import (  # noqa: F401
     CLASS_CONFLICT, CLASS_D_INTER, CLASS_D_PAIR, CLASS_U, CLASS_UD, CLASS_UNLABELED,
-    MODE_P, MODE_SC, TABLE_D, TABLE_U, CammiqError, Context, Index, lib, library_path, pack_isa, pack_reads,
+    MODE_P, MODE_SC, TABLE_D, TABLE_U, CammiqError, Context, Index, MultiContext, lib, library_path, pack_isa, pack_reads,
 )
 
-__all__ = ["Index", "Context", "CammiqError", "lib", "library_path", "MODE_P", "MODE_SC",
+__all__ = ["Index", "Context", "MultiContext", "CammiqError", "lib", "library_path", "MODE_P", "MODE_SC",
            "TABLE_U", "TABLE_D", "pack_reads", "pack_isa"]

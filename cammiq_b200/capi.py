@@ -18,7 +18,7 @@ import numpy as np
 MODE_P, MODE_SC = 0, 1
 TABLE_U, TABLE_D = 0, 1
 CLASS_UNLABELED, CLASS_CONFLICT, CLASS_U, CLASS_D_PAIR, CLASS_UD, CLASS_D_INTER = range(6)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -85,6 +85,17 @@ class Timing(C.Structure):
                 ("h2d_bytes", C.c_uint64)]
 
 
+class MultiInfo(C.Structure):
+    _fields_ = [("n_gpus", C.c_int), ("nccl_version", C.c_int), ("devices", C.c_int * 8),
+                ("shard_reads", C.c_uint64 * 8), ("reduce_ms", C.c_double)]
+
+
+class IlpArgs(C.Structure):
+    _fields_ = [("erate", C.c_double), ("read_length", C.c_uint32), ("wcov_u", C.c_void_p), ("wcov_d1", C.c_void_p),
+                ("wcov_d2", C.c_void_p), ("genome_wcov_u", C.c_void_p), ("genome_wcov_d", C.c_void_p),
+                ("genome_rcount_u", C.c_void_p), ("genome_rcount_d", C.c_void_p)]
+
+
 # every symbol include/cammiq_gpu.h declares: (restype, argtypes)
 SYMBOLS = {
     "cq_last_error": (C.c_char_p, []),
@@ -125,6 +136,18 @@ SYMBOLS = {
     "cq_bench_random_gather": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                           C.POINTER(C.c_double)]),
     "cq_get_device_info": (C.c_int, [C.c_void_p, C.POINTER(DeviceInfo)]),
+    "cq_multi_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cq_multi_destroy": (None, [C.c_void_p]),
+    "cq_multi_n_gpus": (C.c_int, [C.c_void_p]),
+    "cq_multi_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "cq_multi_query": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                 C.c_uint64, C.POINTER(Result)]),
+    "cq_multi_query_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                        C.c_uint64, C.POINTER(Result)]),
+    "cq_multi_reset": (C.c_int, [C.c_void_p]),
+    "cq_multi_ctx": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "cq_multi_get_info": (C.c_int, [C.c_void_p, C.POINTER(MultiInfo)]),
+    "cq_ilp_inputs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(IlpArgs)]),
 }
 
 _LIB = None
@@ -399,6 +422,19 @@ class Context:
                                             1 if persist else 0, C.byref(v)))
         return v.value
 
+    def ilp_inputs(self, erate, read_length):
+        """ILP set-up coefficients from the accumulated rcount (cq_ilp_inputs): per-leaf wcov in
+        file order, per-genome coverage sums and rcount sums."""
+        G, idx = self.n_genomes, self.index
+        out = dict(wcov_u=np.zeros(max(idx.n_leaves_u, 1)), wcov_d1=np.zeros(max(idx.n_leaves_d, 1)),
+                   wcov_d2=np.zeros(max(idx.n_leaves_d, 1)), genome_wcov_u=np.zeros(G + 1), genome_wcov_d=np.zeros(G + 1),
+                   genome_rcount_u=np.zeros(G + 1, dtype=np.uint64), genome_rcount_d=np.zeros(G + 1, dtype=np.uint64))
+        a = IlpArgs(erate=erate, read_length=read_length, **{k: v.ctypes.data for k, v in out.items()})
+        _check(lib().cq_ilp_inputs(self._h, idx._h, C.byref(a)))
+        out["wcov_u"] = out["wcov_u"][:idx.n_leaves_u]
+        out["wcov_d1"], out["wcov_d2"] = out["wcov_d1"][:idx.n_leaves_d], out["wcov_d2"][:idx.n_leaves_d]
+        return out
+
     def device_info(self):
         d = DeviceInfo()
         _check(lib().cq_get_device_info(self._h, C.byref(d)))
@@ -419,6 +455,69 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class MultiContext(Context):
+    """cq_multi: the same interface as Context over several GPUs of one box -- reads sharded,
+    index replicated, one NCCL reduce of the counters (include/cammiq_gpu.h)."""
+
+    def __init__(self, n_gpus, devices=None):  # noqa: super().__init__ would create a single-device context
+        self._m = C.c_void_p()
+        arr = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(lib().cq_multi_create(n_gpus, arr, C.byref(self._m)))
+        self._h = C.c_void_p()
+        self.n_genomes, self.index, self._pinned = 0, None, []
+
+    def upload(self, index, n_genomes):
+        _check(lib().cq_multi_upload(self._m, index._h, n_genomes))
+        self.index, self.n_genomes = index, n_genomes
+        return self
+
+    def reset(self):
+        _check(lib().cq_multi_reset(self._m))
+
+    def _run(self, fn, mode, bases, offsets, lengths, stride, per_read, leaf_cap, want_rcount, pairs_cap, buffers):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(lengths)
+        res, keep = self._result(mode, n, per_read, leaf_cap, want_rcount, pairs_cap, buffers)
+        _check(fn(self._m, mode, bases.ctypes.data, offsets.ctypes.data if offsets is not None else None, stride,
+                  lengths.ctypes.data, n, C.byref(res)))
+        return self._finish(mode, res, keep, n)
+
+    def query(self, mode, bases, offsets, lengths, stride=0, per_read=False, leaf_cap=0, want_rcount=True,
+              pairs_cap=1 << 16, buffers=None):
+        return self._run(lib().cq_multi_query, mode, bases, offsets, lengths, stride, per_read, leaf_cap, want_rcount,
+                         pairs_cap, buffers)
+
+    def query_packed(self, mode, packed, offsets, lengths, stride=0, per_read=False, leaf_cap=0, want_rcount=True,
+                     pairs_cap=1 << 16, buffers=None):
+        return self._run(lib().cq_multi_query_packed, mode, packed, offsets, lengths, stride, per_read, leaf_cap,
+                         want_rcount, pairs_cap, buffers)
+
+    def set_host_packing(self, threads):
+        for i in range(lib().cq_multi_n_gpus(self._m)):
+            h = C.c_void_p()
+            _check(lib().cq_multi_ctx(self._m, i, C.byref(h)))
+            _check(lib().cq_ctx_set_host_packing(h, threads))
+        return self
+
+    def info(self):
+        mi = MultiInfo()
+        _check(lib().cq_multi_get_info(self._m, C.byref(mi)))
+        n = mi.n_gpus
+        return dict(n_gpus=n, nccl_version=mi.nccl_version, devices=list(mi.devices)[:n],
+                    shard_reads=list(mi.shard_reads)[:n], reduce_ms=mi.reduce_ms)
+
+    def close(self):
+        if self._m:
+            lib().cq_multi_destroy(self._m)
+            self._m = C.c_void_p()
+        for p in self._pinned:
+            lib().cq_host_free(p)
+        self._pinned = []
 
 
 def pack_isa():

@@ -16,105 +16,19 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
-#include "../../include/cammiq_gpu.h"
-#include "flat_index.hpp"
+#include "capi_internal.hpp"
 #include "index_codec.hpp"
-#include "pack_reads.hpp"
 #include "scan_kernels.cuh"
 
 using namespace cammiq;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string &msg) {
+int cqFail(int code, const std::string &msg) {
 	g_err = msg;
 	return code;
 }
-
-#define CQ_CUDA(call)                                                                      \
-	do {                                                                                   \
-		cudaError_t e_ = (call);                                                           \
-		if (e_ != cudaSuccess)                                                             \
-			return fail(CQ_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
-	} while (0)
-
-struct cq_index {
-	FlatIndex flat;
-};
-
-struct cq_ctx {
-	int device = 0;
-	int n_sms = 0;
-	cudaStream_t stream = NULL;
-	bool own_stream = false;
-	cudaEvent_t ev[2] = {NULL, NULL}; // H2D bracket of the last cq_reads_stage
-	struct StepEvents { cudaEvent_t e[4]; }; // pack start | scan start | scan end | reduce end
-	std::vector<StepEvents> steps;
-	size_t steps_used = 0;
-	// resident index
-	bool has_index = false;
-	uint32_t h = 0, n_genomes = 0;
-	uint64_t n_leaves_u = 0, n_leaves_d = 0, table_mask = 0;
-	TableSlot *d_table = NULL;
-	uint32_t *d_nodes_u = NULL, *d_nodes_d = NULL, *d_leaf_u_ref = NULL;
-	uint2 *d_leaf_d_ref = NULL;
-	// accumulators
-	unsigned long long *d_counts = NULL; // 2*(G+1)+4
-	uint32_t *d_rcount_u = NULL, *d_rcount_d = NULL;
-	uint32_t *d_partials = NULL;
-	uint32_t *d_spill = NULL; // per-read hit overflow, [max grid warps][32][kHitSpill]
-	uint2 *d_filter = NULL;
-	uint32_t filter_words = 0;
-	int max_grid = 0;
-	unsigned long long *d_probe_count = NULL;
-	int grid = 0;
-	bool smem_counters = true;
-	size_t smem_bytes = 0;
-	// staged reads
-	uint8_t *d_bases = NULL;
-	uint64_t *d_offsets = NULL;
-	uint8_t *d_lengths = NULL;
-	size_t cap_bases = 0, cap_reads_off = 0, cap_reads_len = 0;
-	uint64_t staged_reads = 0, staged_stride = 0, staged_bytes = 0;
-	bool staged_has_offsets = false;
-	uint32_t staged_max_len = 0;
-	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
-	bool staged_packed = false;
-	size_t last_dyn_smem[8] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1,
-		(size_t) -1}; // per kernel variant
-	int last_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	// host->device pipeline of cq_query: kStages chunk buffers rotate through copy and scan
-	static const int kStages = 3;
-	cudaStream_t copy_stream = NULL;
-	cudaEvent_t ev_copied[kStages] = {NULL, NULL, NULL}, ev_free[kStages] = {NULL, NULL, NULL};
-	uint8_t *d_cbases[kStages] = {NULL, NULL, NULL};
-	uint64_t *d_coffsets[kStages] = {NULL, NULL, NULL};
-	uint32_t *d_coffsets32[kStages] = {NULL, NULL, NULL};
-	uint8_t *d_clengths[kStages] = {NULL, NULL, NULL};
-	size_t cap_cbases[kStages] = {0, 0, 0}, cap_coffsets[kStages] = {0, 0, 0}, cap_coffsets32[kStages] = {0, 0, 0},
-		cap_clengths[kStages] = {0, 0, 0};
-	// host packing (cq_ctx_set_host_packing): worker pool + pinned staging of the packed chunks
-	int pack_threads = 0;
-	WorkerPool *pool = NULL;
-	uint8_t *h_pbases[kStages] = {NULL, NULL, NULL};
-	uint8_t *h_plengths[kStages] = {NULL, NULL, NULL};
-	uint32_t *h_poffsets[kStages] = {NULL, NULL, NULL};
-	size_t cap_h_pbases[kStages] = {0, 0, 0}, cap_h_plengths[kStages] = {0, 0, 0}, cap_h_poffsets[kStages] = {0, 0, 0};
-	// SC pair records (device, grows)
-	unsigned long long *d_pairs = NULL;
-	size_t cap_pairs = 0;
-	PairSlot *d_pair_table = NULL, *d_pair_out = NULL; // aggregation scratch of cq_fetch
-	size_t cap_pair_table = 0, cap_pair_out = 0;
-	// per-read outputs (device, sized per call)
-	uint8_t *d_read_class = NULL;
-	uint32_t *d_read_rid_a = NULL, *d_read_rid_b = NULL, *d_nleaf_u = NULL, *d_nleaf_d = NULL,
-		*d_leaf_u = NULL, *d_leaf_d = NULL;
-	size_t cap_read_class = 0, cap_read_rid_a = 0, cap_read_rid_b = 0, cap_nleaf_u = 0, cap_nleaf_d = 0,
-		cap_leaf_u = 0, cap_leaf_d = 0;
-	uint32_t leaf_cap = 0;
-	bool want_per_read = false, want_sets = false;
-	cq_timing timing;
-};
+static int fail(int code, const std::string &msg) { return cqFail(code, msg); }
 
 extern "C" const char *cq_last_error(void) { return g_err.c_str(); }
 extern "C" int cq_abi_version(void) { return CQ_ABI_VERSION; }
@@ -252,8 +166,10 @@ static void freeDevice(cq_ctx *c) {
 	cudaFree(c->d_table); cudaFree(c->d_nodes_u); cudaFree(c->d_nodes_d);
 	cudaFree(c->d_leaf_u_ref); cudaFree(c->d_leaf_d_ref); cudaFree(c->d_counts);
 	cudaFree(c->d_rcount_u); cudaFree(c->d_rcount_d); cudaFree(c->d_partials);
-	cudaFree(c->d_spill); cudaFree(c->d_probe_count); cudaFree(c->d_filter);
+	cudaFree(c->d_spill); cudaFree(c->d_dedup); cudaFree(c->d_probe_count); cudaFree(c->d_filter);
 	c->d_filter = NULL;
+	c->d_dedup = NULL;
+	c->cap_spill = c->cap_dedup = 0;
 	c->d_table = NULL; c->d_nodes_u = c->d_nodes_d = c->d_leaf_u_ref = NULL; c->d_leaf_d_ref = NULL;
 	c->d_counts = NULL; c->d_rcount_u = c->d_rcount_d = c->d_partials = c->d_spill = NULL;
 	c->d_probe_count = NULL;
@@ -463,7 +379,6 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	c->max_grid = kMaxBlocksPerSM * c->n_sms;
 	if (c->smem_counters)
 		CQ_CUDA(cudaMalloc((void **) &c->d_partials, (size_t) c->max_grid * ncnt * sizeof(uint32_t)));
-	CQ_CUDA(cudaMalloc((void **) &c->d_spill, (size_t) c->max_grid * kWarpsPerBlock * 32 * kHitSpill * sizeof(uint32_t)));
 	c->has_index = true;
 	lap("filter, counters, scratch");
 	return cq_reset(c);
@@ -605,12 +520,34 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.read_base = rb.first;
 	sp.lengths = rb.lengths;
 	sp.n_reads = rb.n;
-	// staging buffer: the byte range 32 back-to-back reads of the longest length span
-	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel
-	const uint32_t read_bytes = rb.packed ? (std::max<uint32_t>(rb.max_len, 1) + 3) / 4 : std::max<uint32_t>(rb.max_len, 1);
+	// raw staging buffer: the byte range 32 back-to-back reads of the longest length span
+	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel.
+	// packed buffer: 16 bases per word, two words of slack per read (three-word windows), odd
+	// stride so that the lanes' reads start in different banks
+	const uint32_t longest = std::max<uint32_t>(rb.max_len, 1);
+	const uint32_t read_bytes = rb.packed ? (longest + 3) / 4 : longest;
 	const uint32_t tile_cap = (32 * read_bytes + (rb.packed ? 64 : 32) + 127) & ~127u;
 	sp.tile_cap = tile_cap;
-	const size_t dyn_smem = (size_t) kWarpsPerBlock * tile_cap + c->smem_bytes;
+	sp.words_per_read = (((longest + 15) / 16) + 2) | 1u;
+	const size_t dyn_smem = (size_t) kWarpsPerBlock * (tile_cap + kTileSlack + 32 * sp.words_per_read * 4) + c->smem_bytes;
+	// a read can reach 2 tables x 2 strands x (longest - h + 1) leaves; what exceeds the shared
+	// hit slots spills to global scratch, sized (and grown) for the longest read seen so far
+	const uint32_t max_hits = longest >= c->h ? 4 * (longest - c->h + 1) : 0;
+	sp.spill_stride = max_hits > (uint32_t) kHitSeg ? ((max_hits - kHitSeg + 3) & ~3u) : 4;
+	sp.dedup_slots = 64;
+	while (sp.dedup_slots < 2 * (kHitSeg + sp.spill_stride))
+		sp.dedup_slots <<= 1;
+	{
+		const size_t warps = (size_t) c->max_grid * kWarpsPerBlock;
+		const size_t need_spill = warps * 32 * sp.spill_stride, need_dedup = warps * sp.dedup_slots;
+		if (need_spill > c->cap_spill || need_dedup > c->cap_dedup) {
+			// scratch of launches still in flight: let them finish before it moves
+			CQ_CUDA(cudaStreamSynchronize(c->stream));
+			int rc;
+			if ((rc = ensure(&c->d_spill, &c->cap_spill, need_spill)) != 0) return rc;
+			if ((rc = ensure(&c->d_dedup, &c->cap_dedup, need_dedup)) != 0) return rc;
+		}
+	}
 	sp.smem_counters = c->smem_counters ? 1 : 0;
 	sp.partials = c->d_partials;
 	sp.counts = c->d_counts;
@@ -618,6 +555,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.rcount_d = c->d_rcount_d;
 	sp.pair_records = c->d_pairs;
 	sp.hit_spill = c->d_spill;
+	sp.dedup_sets = c->d_dedup;
 	sp.probe_count = c->d_probe_count;
 	if (c->want_per_read) {
 		sp.read_class = c->d_read_class + rb.first;
@@ -753,17 +691,56 @@ extern "C" int cq_sync(cq_ctx *c) {
 	return CQ_OK;
 }
 
-extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
-	if (c == NULL || !c->has_index || out == NULL)
-		return fail(CQ_ESTATE, "cq_fetch: no index resident or NULL result.");
+// read_cnts_b (query.cpp:994-997): the per-read pair records are folded into (pair, count)
+// entries on the device; only the distinct pairs come back
+int cqCollectPairs(cq_ctx *c, std::vector<cq_pair_count> &out) {
+	out.clear();
+	CQ_CUDA(cudaSetDevice(c->device));
+	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
+	unsigned long long nrec = 0;
+	CQ_CUDA(cudaMemcpyAsync(&nrec, c->d_counts + ncnt + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	if (nrec == 0)
+		return CQ_OK;
+	uint64_t slots = 1024;
+	while (slots < 2 * nrec)
+		slots <<= 1;
+	int rc;
+	if ((rc = ensure(&c->d_pair_table, &c->cap_pair_table, (size_t) slots)) != 0) return rc;
+	if ((rc = ensure(&c->d_pair_out, &c->cap_pair_out, (size_t) nrec + 1)) != 0) return rc;
+	init_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots);
+	aggregate_pairs_kernel<<<(unsigned) ((nrec + 255) / 256), 256, 0, c->stream>>>(c->d_pairs, nrec, c->d_pair_table, slots - 1);
+	unsigned long long *d_n = reinterpret_cast<unsigned long long *>(c->d_pair_out + nrec);
+	CQ_CUDA(cudaMemsetAsync(d_n, 0, sizeof(PairSlot), c->stream));
+	compact_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots, c->d_pair_out, d_n);
+	c->timing.kernel_launches += 3;
+	unsigned long long n_distinct = 0;
+	CQ_CUDA(cudaMemcpyAsync(&n_distinct, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
+	CQ_CUDA(cudaStreamSynchronize(c->stream));
+	std::vector<PairSlot> agg((size_t) n_distinct);
+	if (n_distinct > 0)
+		CQ_CUDA(cudaMemcpy(agg.data(), c->d_pair_out, (size_t) n_distinct * sizeof(PairSlot), cudaMemcpyDeviceToHost));
+	out.resize(agg.size());
+	for (size_t i = 0; i < agg.size(); i++) {
+		out[i].a = (uint32_t) (agg[i].key >> 32);
+		out[i].b = (uint32_t) agg[i].key;
+		out[i].count = agg[i].count;
+	}
+	return CQ_OK;
+}
+
+static bool pairLess(const cq_pair_count &x, const cq_pair_count &y) { return x.a != y.a ? x.a < y.a : x.b < y.b; }
+
+int cqFetchFrom(cq_ctx *c, int mode, const unsigned long long *d_counts, const uint32_t *d_rcount_u, const uint32_t *d_rcount_d,
+		cq_result *out, bool with_pairs) {
 	CQ_CUDA(cudaSetDevice(c->device));
 	const size_t G1 = (size_t) c->n_genomes + 1, ncnt = 2 * G1;
 	std::vector<unsigned long long> counts(ncnt + 4);
-	CQ_CUDA(cudaMemcpyAsync(counts.data(), c->d_counts, (ncnt + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
+	CQ_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (ncnt + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
 	if (out->rcount_u && mode == CQ_MODE_P && c->n_leaves_u)
-		CQ_CUDA(cudaMemcpyAsync(out->rcount_u, c->d_rcount_u, c->n_leaves_u * 4, cudaMemcpyDeviceToHost, c->stream));
+		CQ_CUDA(cudaMemcpyAsync(out->rcount_u, d_rcount_u, c->n_leaves_u * 4, cudaMemcpyDeviceToHost, c->stream));
 	if (out->rcount_d && mode == CQ_MODE_P && c->n_leaves_d)
-		CQ_CUDA(cudaMemcpyAsync(out->rcount_d, c->d_rcount_d, c->n_leaves_d * 4, cudaMemcpyDeviceToHost, c->stream));
+		CQ_CUDA(cudaMemcpyAsync(out->rcount_d, d_rcount_d, c->n_leaves_d * 4, cudaMemcpyDeviceToHost, c->stream));
 	CQ_CUDA(cudaStreamSynchronize(c->stream));
 	if (out->cnt_u) memcpy(out->cnt_u, counts.data(), G1 * 8);
 	if (out->cnt_d) memcpy(out->cnt_d, counts.data() + G1, G1 * 8);
@@ -771,38 +748,14 @@ extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
 	out->nconf = counts[ncnt + 1];
 	out->n_invalid = counts[ncnt + 2];
 	out->n_pairs = 0;
-	if (mode == CQ_MODE_SC) {
-		// read_cnts_b (query.cpp:994-997): the per-read pair records are folded into (pair, count)
-		// entries on the device; only the distinct pairs come back and are put in (a, b) order here
-		const uint64_t nrec = counts[ncnt + 3];
-		std::vector<PairSlot> agg;
-		if (nrec > 0) {
-			uint64_t slots = 1024;
-			while (slots < 2 * nrec)
-				slots <<= 1;
-			int rc;
-			if ((rc = ensure(&c->d_pair_table, &c->cap_pair_table, (size_t) slots)) != 0) return rc;
-			if ((rc = ensure(&c->d_pair_out, &c->cap_pair_out, (size_t) nrec + 1)) != 0) return rc;
-			init_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots);
-			aggregate_pairs_kernel<<<(unsigned) ((nrec + 255) / 256), 256, 0, c->stream>>>(c->d_pairs, nrec, c->d_pair_table, slots - 1);
-			unsigned long long *d_n = reinterpret_cast<unsigned long long *>(c->d_pair_out + nrec);
-			CQ_CUDA(cudaMemsetAsync(d_n, 0, sizeof(PairSlot), c->stream));
-			compact_pairs_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, c->stream>>>(c->d_pair_table, slots, c->d_pair_out, d_n);
-			c->timing.kernel_launches += 3;
-			unsigned long long n_distinct = 0;
-			CQ_CUDA(cudaMemcpyAsync(&n_distinct, d_n, 8, cudaMemcpyDeviceToHost, c->stream));
-			CQ_CUDA(cudaStreamSynchronize(c->stream));
-			agg.resize((size_t) n_distinct);
-			if (n_distinct > 0)
-				CQ_CUDA(cudaMemcpy(agg.data(), c->d_pair_out, (size_t) n_distinct * sizeof(PairSlot), cudaMemcpyDeviceToHost));
-			std::sort(agg.begin(), agg.end(), [](const PairSlot &x, const PairSlot &y) { return x.key < y.key; });
-		}
+	if (mode == CQ_MODE_SC && with_pairs) {
+		std::vector<cq_pair_count> agg;
+		int rc = cqCollectPairs(c, agg);
+		if (rc != 0) return rc;
+		std::sort(agg.begin(), agg.end(), pairLess);
 		const uint64_t np = agg.size();
-		for (uint64_t i = 0; i < np && out->pairs && i < out->pairs_cap; i++) {
-			out->pairs[i].a = (uint32_t) (agg[i].key >> 32);
-			out->pairs[i].b = (uint32_t) agg[i].key;
-			out->pairs[i].count = agg[i].count;
-		}
+		for (uint64_t i = 0; i < np && out->pairs && i < out->pairs_cap; i++)
+			out->pairs[i] = agg[i];
 		out->n_pairs = np;
 		if (out->pairs && np > out->pairs_cap)
 			return fail(CQ_EINVAL, "cq_fetch: pairs_cap too small for the pair map.");
@@ -810,7 +763,15 @@ extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
 	return CQ_OK;
 }
 
+extern "C" int cq_fetch(cq_ctx *c, int mode, cq_result *out) {
+	if (c == NULL || !c->has_index || out == NULL)
+		return fail(CQ_ESTATE, "cq_fetch: no index resident or NULL result.");
+	return cqFetchFrom(c, mode, c->d_counts, c->d_rcount_u, c->d_rcount_d, out, true);
+}
+
 static int fetchPerRead(cq_ctx *c, uint64_t n, cq_result *out) {
+	if ((c->want_per_read || c->want_sets) && n > 0)
+		CQ_CUDA(cudaStreamSynchronize(c->stream)); // the copies below run on the default stream
 	if (c->want_per_read && n > 0) {
 		CQ_CUDA(cudaMemcpy(out->read_class, c->d_read_class, n, cudaMemcpyDeviceToHost));
 		CQ_CUDA(cudaMemcpy(out->read_rid_a, c->d_read_rid_a, n * 4, cudaMemcpyDeviceToHost));
@@ -951,19 +912,21 @@ static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uin
 	return CQ_OK;
 }
 
-static int queryHost(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
-		const uint8_t *lengths, uint64_t n_reads, cq_result *out, const char *who) {
+int cqSubmitHost(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *per_read, const char *who) {
 	if (c == NULL || !c->has_index)
 		return fail(CQ_ESTATE, std::string(who) + ": no index resident (call cq_index_upload first).");
-	if (out == NULL || (mode != CQ_MODE_P && mode != CQ_MODE_SC))
-		return fail(CQ_EINVAL, std::string(who) + ": NULL result or bad mode.");
+	if (mode != CQ_MODE_P && mode != CQ_MODE_SC)
+		return fail(CQ_EINVAL, std::string(who) + ": bad mode.");
 	if (n_reads > 0 && (bases == NULL || lengths == NULL))
 		return fail(CQ_EINVAL, std::string(who) + ": NULL read buffers.");
+	if (n_reads >= (1ull << 36))
+		return fail(CQ_EINVAL, std::string(who) + ": more than 2^36 reads in one call.");
 	CQ_CUDA(cudaSetDevice(c->device));
-	auto t0 = std::chrono::high_resolution_clock::now();
-	c->want_per_read = out->read_class != NULL && out->read_rid_a != NULL && out->read_rid_b != NULL;
-	c->want_sets = out->leaf_cap > 0 && out->read_nleaf_u && out->read_nleaf_d && out->read_leaf_u && out->read_leaf_d;
-	c->leaf_cap = c->want_sets ? out->leaf_cap : 0;
+	c->want_per_read = per_read != NULL && per_read->read_class != NULL && per_read->read_rid_a != NULL && per_read->read_rid_b != NULL;
+	c->want_sets = per_read != NULL && per_read->leaf_cap > 0 && per_read->read_nleaf_u && per_read->read_nleaf_d &&
+		per_read->read_leaf_u && per_read->read_leaf_d;
+	c->leaf_cap = c->want_sets ? per_read->leaf_cap : 0;
 	int rc = prepareOutputs(c, mode, n_reads);
 	cudaEvent_t *sev = NULL;
 	if (rc == 0) rc = beginStep(c, &sev);
@@ -983,11 +946,22 @@ static int queryHost(cq_ctx *c, int mode, bool packed, const uint8_t *bases, con
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
 	CQ_CUDA(cudaEventRecord(c->ev[1], c->stream));
 	CQ_CUDA(cudaGetLastError());
-	auto t1 = std::chrono::high_resolution_clock::now();
-	rc = cq_fetch(c, mode, out);
-	if (rc == 0) rc = fetchPerRead(c, n_reads, out);
+	if (per_read != NULL)
+		rc = fetchPerRead(c, n_reads, per_read);
 	c->want_per_read = c->want_sets = false;
 	c->leaf_cap = 0;
+	return rc;
+}
+
+static int queryHost(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out, const char *who) {
+	if (out == NULL)
+		return fail(CQ_EINVAL, std::string(who) + ": NULL result.");
+	auto t0 = std::chrono::high_resolution_clock::now();
+	int rc = cqSubmitHost(c, mode, packed, bases, offsets, stride, lengths, n_reads, out, who);
+	if (rc != 0) return rc;
+	auto t1 = std::chrono::high_resolution_clock::now();
+	rc = cq_fetch(c, mode, out);
 	auto t2 = std::chrono::high_resolution_clock::now();
 	c->timing.d2h_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
 	c->timing.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
@@ -1042,6 +1016,84 @@ extern "C" int cq_host_alloc(size_t bytes, void **out) {
 extern "C" void cq_host_free(void *p) {
 	if (p != NULL)
 		cudaFreeHost(p);
+}
+
+// ILP input assembly on the device (query.cpp:1154-1181).
+extern "C" int cq_ilp_inputs(cq_ctx *c, const cq_index *idx, cq_ilp_args *io) {
+	if (c == NULL || !c->has_index || idx == NULL || io == NULL)
+		return fail(CQ_ESTATE, "cq_ilp_inputs: NULL argument or no index resident.");
+	if (io->read_length == 0)
+		return fail(CQ_EINVAL, "cq_ilp_inputs: read_length is 0.");
+	const FlatIndex &f = idx->flat;
+	if (f.u.numLeaves() != c->n_leaves_u || f.d.numLeaves() != c->n_leaves_d)
+		return fail(CQ_EINVAL, "cq_ilp_inputs: this index is not the one resident on the context.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	const size_t G1 = (size_t) c->n_genomes + 1;
+	for (int t = 0; t < 2; t++) {
+		const DecodedIndex &x = t == 0 ? f.u : f.d;
+		const uint64_t n = x.numLeaves();
+		double *h_w1 = t == 0 ? io->wcov_u : io->wcov_d1, *h_w2 = t == 0 ? NULL : io->wcov_d2;
+		double *h_gw = t == 0 ? io->genome_wcov_u : io->genome_wcov_d;
+		uint64_t *h_gr = t == 0 ? io->genome_rcount_u : io->genome_rcount_d;
+		if (h_gw) memset(h_gw, 0, G1 * sizeof(double));
+		if (h_gr) memset(h_gr, 0, G1 * sizeof(uint64_t));
+		if (n == 0)
+			continue;
+		// leaf fields the scan does not need live on the host; they travel for this call only
+		uint16_t *d_uc1 = NULL, *d_uc2 = NULL;
+		uint8_t *d_depth = NULL;
+		double *d_w1 = NULL, *d_w2 = NULL, *d_gw = NULL;
+		unsigned long long *d_gr = NULL;
+		int rc = CQ_OK;
+		auto release = [&]() {
+			cudaFree(d_uc1); cudaFree(d_uc2); cudaFree(d_depth); cudaFree(d_w1); cudaFree(d_w2); cudaFree(d_gw); cudaFree(d_gr);
+		};
+#define CQ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(CQ_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+		CQ_TRY(cudaMalloc((void **) &d_uc1, n * 2));
+		CQ_TRY(cudaMalloc((void **) &d_depth, n));
+		CQ_TRY(cudaMalloc((void **) &d_w1, n * 8));
+		CQ_TRY(cudaMalloc((void **) &d_gw, G1 * 8));
+		CQ_TRY(cudaMalloc((void **) &d_gr, G1 * 8));
+		CQ_TRY(cudaMemcpyAsync(d_uc1, x.ucount1.data(), n * 2, cudaMemcpyHostToDevice, c->stream));
+		CQ_TRY(cudaMemcpyAsync(d_depth, x.depth.data(), n, cudaMemcpyHostToDevice, c->stream));
+		CQ_TRY(cudaMemsetAsync(d_gw, 0, G1 * 8, c->stream));
+		CQ_TRY(cudaMemsetAsync(d_gr, 0, G1 * 8, c->stream));
+		if (t == 1) {
+			CQ_TRY(cudaMalloc((void **) &d_uc2, n * 2));
+			CQ_TRY(cudaMalloc((void **) &d_w2, n * 8));
+			CQ_TRY(cudaMemcpyAsync(d_uc2, x.ucount2.data(), n * 2, cudaMemcpyHostToDevice, c->stream));
+		}
+		IlpParams q;
+		memset(&q, 0, sizeof(q));
+		// the resident leaf records already hold the genome ids: u32 per U leaf, {u32, u32} per D leaf
+		q.ref1 = t == 0 ? c->d_leaf_u_ref : reinterpret_cast<const uint32_t *>(c->d_leaf_d_ref);
+		q.ref2 = t == 0 ? NULL : reinterpret_cast<const uint32_t *>(c->d_leaf_d_ref) + 1;
+		q.ref_stride = t == 0 ? 1 : 2;
+		q.ucount1 = d_uc1;
+		q.ucount2 = d_uc2;
+		q.depth = d_depth;
+		q.rcount = t == 0 ? c->d_rcount_u : c->d_rcount_d;
+		q.n = n;
+		q.n_genomes = c->n_genomes;
+		q.rl = io->read_length;
+		q.one_minus_e = 1 - io->erate;
+		q.wcov1 = d_w1;
+		q.wcov2 = d_w2;
+		q.genome_wcov = d_gw;
+		q.genome_rcount = d_gr;
+		ilp_inputs_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, c->stream>>>(q);
+		c->timing.kernel_launches++;
+		CQ_TRY(cudaGetLastError());
+		if (h_w1) CQ_TRY(cudaMemcpyAsync(h_w1, d_w1, n * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (h_w2) CQ_TRY(cudaMemcpyAsync(h_w2, d_w2, n * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (h_gw) CQ_TRY(cudaMemcpyAsync(h_gw, d_gw, G1 * 8, cudaMemcpyDeviceToHost, c->stream));
+		if (h_gr) CQ_TRY(cudaMemcpyAsync(h_gr, d_gr, G1 * 8, cudaMemcpyDeviceToHost, c->stream));
+		CQ_TRY(cudaStreamSynchronize(c->stream));
+#undef CQ_TRY
+		release();
+		(void) rc;
+	}
+	return CQ_OK;
 }
 
 extern "C" int cq_get_device_counters(cq_ctx *c, cq_device_counters *out) {
@@ -1145,13 +1197,23 @@ extern "C" int cq_bench_random_gather(cq_ctx *c, uint64_t region_bytes, int acce
 		CQ_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
 	}
 	const uint64_t mask = (region_bytes - 1) & ~(uint64_t) (access_bytes - 1);
-	const int grid = c->n_sms * 8;
+	// CAMMIQ_GATHER_SMEM (bytes per block) / CAMMIQ_GATHER_BLOCKS (per SM): the same gathers with part
+	// of the SM's unified L1 / shared memory taken away -- how much L1 the in-flight loads need
+	const size_t dsm = getenv("CAMMIQ_GATHER_SMEM") ? (size_t) atol(getenv("CAMMIQ_GATHER_SMEM")) : 0;
+	const int per_sm = getenv("CAMMIQ_GATHER_BLOCKS") ? std::max(1, atoi(getenv("CAMMIQ_GATHER_BLOCKS"))) : 8;
+	const int grid = c->n_sms * per_sm;
+	if (dsm > 0) {
+		cudaFuncSetAttribute((const void *) random_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);
+	}
 	auto launch = [&](uint64_t seed) {
 		switch (access_bytes) {
-		case 4: random_gather_kernel<4><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
-		case 8: random_gather_kernel<8><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
-		case 16: random_gather_kernel<16><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
-		default: random_gather_kernel<32><<<grid, 256, 0, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		case 4: random_gather_kernel<4><<<grid, 256, dsm, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		case 8: random_gather_kernel<8><<<grid, 256, dsm, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		case 16: random_gather_kernel<16><<<grid, 256, dsm, c->stream>>>(region, mask, n_probes, seed, sink); break;
+		default: random_gather_kernel<32><<<grid, 256, dsm, c->stream>>>(region, mask, n_probes, seed, sink); break;
 		}
 	};
 	launch(1);

@@ -13,7 +13,7 @@
 namespace cammiq {
 
 uint64_t FlatIndex::deviceBytes() const {
-	return table.size() * sizeof(TableSlot) + filter.size() * 8 + (u.nodes.size() + d.nodes.size()) * 4 +
+	return table.size() * sizeof(TableBucket) + filter.size() * 8 + (u.nodes.size() + d.nodes.size()) * 4 +
 		u.numLeaves() * 4 + d.numLeaves() * 8 + (u.numLeaves() + d.numLeaves()) * 4;
 }
 
@@ -24,22 +24,42 @@ unsigned flattenThreads() {
 	return std::max(1u, std::min(n, 16u));
 }
 
-// Insert (or find) key; returns the slot.  Linear probing by bucket.
-inline TableSlot *probeInsert(RawArray<TableSlot> &t, uint64_t mask, uint32_t h, uint64_t key, bool &fresh) {
+// A bucket slot: where a key's two root refs live.
+struct SlotRef {
+	TableBucket *b;
+	int k;
+};
+
+// Find or place `key` in bucket b.  Returns the slot index, or -1 when the bucket is full of
+// other keys (the caller raises the bucket's overflow flag and moves on).
+inline int bucketInsert(TableBucket &b, uint64_t key, bool &fresh) {
+	const uint64_t tag = key | kKeyOccupied;
+	for (int k = 0; k < kSlotsPerBucket; k++) {
+		const uint64_t have = b.key[k] & ~kBucketOverflow;
+		if (have == tag) {
+			fresh = false;
+			return k;
+		}
+		if (have == 0) {
+			b.key[k] |= tag;
+			fresh = true;
+			return k;
+		}
+	}
+	return -1;
+}
+
+// Insert (or find) key; returns the slot.  Linear probing by bucket; every full bucket passed
+// on the way gets its overflow flag, so lookups know to look further.
+inline SlotRef probeInsert(RawArray<TableBucket> &t, uint64_t mask, uint32_t h, uint64_t key, bool &fresh) {
 	uint64_t b = homeBucketHost(key, h, mask);
 	for (;;) {
-		TableSlot *s = &t[b * kSlotsPerBucket];
-		for (int i = 0; i < kSlotsPerBucket; i++) {
-			if (s[i].key == key) {
-				fresh = false;
-				return &s[i];
-			}
-			if (s[i].key == kEmptyKey) {
-				s[i].key = key;
-				fresh = true;
-				return &s[i];
-			}
+		const int k = bucketInsert(t[b], key, fresh);
+		if (k >= 0) {
+			SlotRef r = {&t[b], k};
+			return r;
 		}
+		t[b].key[0] |= kBucketOverflow;
 		b = (b + 1) & mask;
 	}
 }
@@ -66,10 +86,10 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 		nb <<= 1;
 	out.n_table_buckets = nb;
 	// the table is a few GB: allocate it raw and first-touch it from all threads
-	if (!out.table.alloc(nb * kSlotsPerBucket))
+	if (!out.table.alloc(nb))
 		throw std::bad_alloc();
 	{
-		const TableSlot empty = {kEmptyKey, kRefNone, kRefNone};
+		const TableBucket empty = {{0, 0}, {{kRefNone, kRefNone}, {kRefNone, kRefNone}}};
 		const unsigned Ti = flattenThreads();
 		std::vector<std::thread> pool;
 		for (unsigned p = 0; p < Ti; p++)
@@ -133,33 +153,27 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 							bad_key = true;
 							return;
 						}
-						TableSlot *hit = NULL;
-						for (uint64_t b = e.b; b < hi && hit == NULL; b++) {
-							TableSlot *s = &out.table[b * kSlotsPerBucket];
-							for (int k = 0; k < kSlotsPerBucket; k++) {
-								if (s[k].key == key) {
-									hit = &s[k];
-									break;
-								}
-								if (s[k].key == kEmptyKey) {
-									s[k].key = key;
-									fresh++;
-									hit = &s[k];
-									break;
-								}
-							}
+						// probe inside the owned range; a bucket that is left behind full gets its
+						// overflow flag (also when the key ends up deferred: it will lie further on)
+						SlotRef hit = {NULL, 0};
+						for (uint64_t b = e.b; b < hi && hit.b == NULL; b++) {
+							bool is_new = false;
+							const int k = bucketInsert(out.table[b], key, is_new);
+							if (k >= 0) {
+								hit.b = &out.table[b];
+								hit.k = k;
+								fresh += is_new ? 1 : 0;
+							} else
+								out.table[b].key[0] |= kBucketOverflow;
 						}
-						if (hit == NULL) {
+						if (hit.b == NULL) {
 							Deferred df = {(uint8_t) t, e.i};
 							deferred[p].push_back(df);
 							return;
 						}
 						// a repeated key inside one file: the later bucket replaces the earlier one, as
 						// map64[bucket] = root does (hashtrie.cpp:500)
-						if (t == 0)
-							hit->u_ref = x.bucket_root[e.i];
-						else
-							hit->d_ref = x.bucket_root[e.i];
+						hit.b->ref[hit.k][t] = x.bucket_root[e.i];
 					};
 					uint64_t queued = 0;
 					for (size_t i = 0; i < x.bucket_key.size(); i++) {
@@ -190,12 +204,11 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 		for (const Deferred &df : deferred[p]) {
 			const DecodedIndex &x = df.table == 0 ? u : d;
 			bool fresh;
-			TableSlot *s = probeInsert(out.table, mask, u.hash_len, x.bucket_key[df.index], fresh);
+			// the flags of the owner's range are already raised; from the range end on, the key
+			// wraps into buckets of another (finished) range
+			SlotRef s = probeInsert(out.table, mask, u.hash_len, x.bucket_key[df.index], fresh);
 			n_keys += fresh ? 1 : 0;
-			if (df.table == 0)
-				s->u_ref = x.bucket_root[df.index];
-			else
-				s->d_ref = x.bucket_root[df.index];
+			s.b->ref[s.k][df.table] = x.bucket_root[df.index];
 		}
 	}
 	out.n_keys = n_keys;
@@ -211,6 +224,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 	fi.filter.clear();
 	fi.filter.shrink_to_fit();
+	fi.filter_words = 0;
 	if (max_bytes < 8192)
 		return;
 	// 16 bits per key when the budget allows, never fewer than kFilterMinBitsPerKey
@@ -227,15 +241,16 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 	for (unsigned p = 0; p < T; p++)
 		pool.emplace_back([&, p]() {
 			const size_t lo = fi.table.size() * p / T, hi = fi.table.size() * (p + 1) / T;
-			for (size_t i = lo; i < hi; i++) {
-				if (fi.table[i].key == kEmptyKey)
-					continue;
-				uint32_t A, B;
-				const uint64_t key = fi.table[i].key, canon = canonicalKeyHost(key, fi.hash_len);
-				filterHash(canon, A, B);
-				__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_words)],
-					filterMask(key == canon ? B : filterOtherPattern(B)), __ATOMIC_RELAXED);
-			}
+			for (size_t i = lo; i < hi; i++)
+				for (int k = 0; k < kSlotsPerBucket; k++) {
+					const uint64_t stored = fi.table[i].key[k] & ~kBucketOverflow;
+					if (stored == 0)
+						continue;
+					uint32_t A, B;
+					const uint64_t key = stored & ~kKeyOccupied, canon = canonicalKeyHost(key, fi.hash_len);
+					filterHash(canon, A, B);
+					__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_words)], filterMask(B), __ATOMIC_RELAXED);
+				}
 		});
 	for (auto &th : pool) th.join();
 }
@@ -248,23 +263,21 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 		const uint64_t canon = canonicalKeyHost(bucket, fi.hash_len);
 		filterHash(canon, A, B);
 		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_words)];
-		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), bucket == canon ? B : filterOtherPattern(B)))
+		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
 			return UINT64_MAX;
 	}
 	uint64_t b = homeBucketHost(bucket, fi.hash_len, mask);
 	uint32_t ref = kRefNone;
+	const uint64_t tag = bucket | kKeyOccupied;
 	for (;;) {
-		const TableSlot *s = &fi.table[b * kSlotsPerBucket];
-		bool hit = false, has_empty = false;
-		for (int i = 0; i < kSlotsPerBucket; i++) {
-			if (s[i].key == bucket) {
-				ref = table == CQ_TABLE_U ? s[i].u_ref : s[i].d_ref;
+		const TableBucket &tb = fi.table[b];
+		bool hit = false;
+		for (int k = 0; k < kSlotsPerBucket; k++)
+			if ((tb.key[k] & ~kBucketOverflow) == tag) {
+				ref = tb.ref[k][table == CQ_TABLE_U ? 0 : 1];
 				hit = true;
 			}
-			if (s[i].key == kEmptyKey)
-				has_empty = true;
-		}
-		if (hit || has_empty)
+		if (hit || !(tb.key[0] & kBucketOverflow))
 			break;
 		b = (b + 1) & mask;
 	}

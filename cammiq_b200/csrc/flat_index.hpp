@@ -1,10 +1,14 @@
 // Flattened, device-ready form of the two CAMMiQ indices.
 //
-//   prefix table   open addressing over 32-byte buckets (= one DRAM/L2 sector), two slots
-//                  per bucket: {key:u64, u_ref:u32, d_ref:u32}.  U and D share the hash
-//                  length (query.cpp:460), so ONE probe answers both tables.  Linear probing
-//                  by bucket; a lookup stops at the first bucket that holds the key or has a
-//                  free slot, so at the default load factor a miss costs one sector.
+//   prefix table   open addressing over 32-byte buckets (= one DRAM/L2 sector), two slots per
+//                  bucket, keys first: {key0, key1, (u_ref0, d_ref0), (u_ref1, d_ref1)}.  U and D
+//                  share the hash length (query.cpp:460), so ONE probe answers both tables, and
+//                  the 16 bytes of keys alone decide whether a read position is a candidate
+//                  (what phase 1 of the scan loads when no filter fronts the table).  Linear
+//                  probing by bucket; bit 63 of key0 is the bucket's OVERFLOW flag: some key whose
+//                  probe sequence passed this bucket lies further on.  A lookup stops at the first
+//                  bucket that holds the key or whose flag is clear, so a miss costs one sector
+//                  unless a key really spilled past the bucket (2 % of buckets at load 0.30).
 //   trie nodes     per table, 4 child refs (16 bytes) per internal node; only buckets whose
 //                  root is not already a leaf have any (rare when h == k).
 //   leaf refs      per table, the genome id(s) the classification needs: u32 for U,
@@ -23,12 +27,13 @@
 
 namespace cammiq {
 
-struct TableSlot {
-	uint64_t key;
-	uint32_t u_ref;
-	uint32_t d_ref;
+struct TableBucket {
+	uint64_t key[2];    // 0 = free slot, else kKeyOccupied | h-mer (h <= 31: 62 bits); key[0] bit 63 = overflow flag
+	uint32_t ref[2][2]; // [slot][0 = U root, 1 = D root]
 };
-static const uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+static const uint64_t kKeyOccupied = 1ull << 62;
+static const uint64_t kBucketOverflow = 1ull << 63;
+static const uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull; // free entry of the SC pair table (scan_kernels.cuh)
 static const int kSlotsPerBucket = 2;
 
 // Bucket index of a key; the same function runs on the host (flatten, find_host) and in the
@@ -46,15 +51,16 @@ inline uint64_t mixKey(uint64_t x) {
 }
 
 // L2-resident membership filter in front of the table: register-blocked Bloom filter, one
-// 64-bit word per key, two bits in each 32-bit half.  ~98-99% of probes miss (SURVEY.md
-// Appendix A.6); a filter that fits the B200's L2 (random gathers over <= 64 MB run at
-// ~285 G/s versus ~45 G sectors/s from HBM, profiles/r01_microbench_gather.json) answers
-// them without touching DRAM.  The filter hash is deliberately lean (6 integer multiplies,
-// 32-bit only): it runs twice per read position.  Word index = top bits of A, bit
-// selectors = top 20 bits of B; (f, g) keep the 62-bit key injective before mixing.
-// The filter is keyed by the CANONICAL h-mer, min(key, reverse complement of key): the scan
-// holds both strands' hashes of a window anyway (hf, hr), so one filter probe per read
-// position answers both strands -- half the L2 requests of probing each strand's hash.
+// 64-bit word per key, four bits of it set.  ~98-99% of probes miss; a
+// filter that fits the B200's L2 (random gathers over <= 64 MB run at ~285 G/s versus ~45 G
+// sectors/s from HBM, profiles/r01_microbench_gather.json) answers them without touching DRAM.
+// The filter is keyed by the CANONICAL h-mer, min(key, reverse complement of key): the scan holds
+// both strands' hashes of a window anyway (hf, hr), so ONE probe and ONE test per read position
+// answer both strands; which orientation is the key is sorted out by the table probe of the few
+// positions that pass (the bucket of a key and of its reverse complement is the same one).
+// The hash runs once per read position and is deliberately lean: two independent multiply-add
+// hashes of the key's 32-bit halves (4 IMAD), the word index from the high bits of the first,
+// the bit selectors from the second.
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
 static const uint32_t kFilterMinBitsPerKey = 8;
 
@@ -80,22 +86,10 @@ inline uint64_t homeBucketHost(uint64_t key, uint32_t h, uint64_t mask) { return
 __host__ __device__
 #endif
 inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
-	uint32_t lo = (uint32_t) key, hi = (uint32_t) (key >> 32);
-	uint32_t f = lo ^ (hi * 0x9E3779B1u);
-	uint32_t g = hi ^ (lo * 0x85EBCA77u);
-	A = f * 0xC2B2AE3Du;
-	A ^= A >> 15;
-	A *= 0x27D4EB2Fu;
-	B = (g ^ A) * 0x165667B1u;
+	const uint32_t lo = (uint32_t) key, hi = (uint32_t) (key >> 32);
+	A = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+	B = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
 }
-// The filter remembers WHICH orientation of the canonical h-mer is a key: a key equal to its
-// canonical form sets the bit pattern of B, a key that is the reverse complement of its
-// canonical form sets the pattern of filterOtherPattern(B).  A probe tests both patterns of
-// the one word it loaded and queues only the strand(s) that can hold the key.
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-inline uint32_t filterOtherPattern(uint32_t B) { return B * 0x58367ADAu + 0x9E3779B9u; } // even multiplier: bit 31 of B (the scan's orientation flag) has no influence
 // word index for a filter of `words` words (any count below 2^32): the high half of A * words
 #if defined(__CUDACC__)
 __host__ __device__
@@ -175,8 +169,8 @@ struct FlatIndex {
 	uint32_t hash_len = 0;
 	uint64_t n_table_buckets = 0; // power of two
 	uint64_t n_keys = 0;
-	RawArray<TableSlot> table;    // n_table_buckets * kSlotsPerBucket
-	std::vector<uint64_t> filter; // power-of-two words, empty = no filter (index too large for L2)
+	RawArray<TableBucket> table;  // n_table_buckets
+	std::vector<uint64_t> filter; // any multiple of 128 words, empty = no filter (index too large for L2)
 	uint32_t filter_words = 0;    // = filter.size()
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
 	double decode_ms = 0, flatten_ms = 0;

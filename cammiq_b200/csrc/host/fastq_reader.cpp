@@ -159,11 +159,26 @@ bool readFastq(const std::string &path, size_t min_len, ReadSet &out, int thread
 			li++;
 		}
 	});
-	// a last record cut off after its header: getline yields an empty bases line (query.cpp:381)
+	// A last record cut off after its header (query.cpp:380-381).  With a final newline the second
+	// getline extracts nothing and leaves an EMPTY bases line; without one the first getline has
+	// already hit end-of-file, the second does not touch its string, and the HEADER TEXT is what
+	// the reference stores as the read.
 	const uint64_t n_lines = before[(size_t) T] + (data[size - 1] != '\n' ? 1 : 0);
-	if ((n_lines & 3) == 1 && min_len == 0) {
-		LineRef r = {data + size, 0};
-		slices[(size_t) T - 1].reads.push_back(r);
+	if ((n_lines & 3) == 1) {
+		uint64_t start = size;
+		if (data[size - 1] != '\n') {
+			start = size - 1;
+			while (start > 0 && data[start - 1] != '\n')
+				start--;
+		}
+		const uint64_t rl = size - start;
+		if (rl >= min_len) {
+			Slice &s = slices[(size_t) T - 1];
+			LineRef r = {data + start, rl};
+			s.reads.push_back(r);
+			s.packed_bytes += packedBytes((uint8_t) rl);
+			s.total_length += rl;
+		}
 	}
 
 	std::vector<uint64_t> read_base((size_t) T + 1, 0), byte_base((size_t) T + 1, 0);

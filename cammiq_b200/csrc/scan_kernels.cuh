@@ -1,21 +1,31 @@
 // sm_100a kernels of the read-matching path.
 //
-//   scan_reads_kernel      A1-A8 in one launch, persistent grid: every WARP pulls sub-tiles of
-//                          32 reads (ASCII, or 2-bit packed by the host) into its own shared-
-//                          memory buffer with one TMA bulk copy (cp.async.bulk + mbarrier), then
-//                            phase 1 (thread per read): decode each base to its 2-bit code,
-//                              roll the h-base prefix hash of BOTH strands in registers and
-//                              test the canonical h-mer of every position against the L2-
-//                              resident membership filter (or the prefix table itself when the
-//                              index is too large for a filter); positives go to a per-warp
-//                              queue,
-//                            phase 2 (warp-cooperative): queued candidates probe the prefix
-//                              table in HBM (one 32-byte sector = one bucket) and descend the
-//                              CSR trie; leaves land in per-read hit lists,
-//                            phase 3 (thread per read): leaf set -> decision -> counters.
+//   scan_reads_kernel      A1-A8 in one launch, persistent grid.  Every WARP owns tiles of 32
+//                          reads and runs four steps per tile, with no block-wide barrier:
+//                            stage    one TMA bulk copy (cp.async.bulk + the warp's mbarrier)
+//                                     brings the tile's bytes into shared memory; lane r turns
+//                                     read r into 2-bit codes, 16 bases per 32-bit word (ASCII
+//                                     input is decoded and validated here), after which the raw
+//                                     buffer is free and the NEXT tile's copy is issued at once;
+//                            phase 1  the tile's read positions are cut into strips of 8; a lane
+//                                     takes a strip, extracts its first h-mer from three packed
+//                                     words, rolls the hashes of BOTH strands through the strip
+//                                     in registers and issues all 8 probes (membership-filter
+//                                     words in L2, or the 16 key bytes of the table bucket when
+//                                     the index is too large for a filter) before testing any of
+//                                     them; positives are compacted into the warp's queue by
+//                                     ballot, no atomics;
+//                            phase 2  one queued candidate per lane: probe the prefix table in
+//                                     HBM (one 32-byte sector = one bucket), descend the CSR
+//                                     trie, append leaves to the owning read's hit list;
+//                            phase 3  lane r: leaf set of read r -> decision -> counters.  Reads
+//                                     with long hit lists are deduplicated by the whole warp
+//                                     through a hash set; genome counters are combined across
+//                                     the warp with match_any before they reach shared memory.
 //   reduce_partials_kernel per-block genome-count partials -> 64-bit totals (no atomics)
 //   init_pairs_kernel, aggregate_pairs_kernel, compact_pairs_kernel
 //                          query64_sc's pair map: per-read pair records -> (pair, count) entries
+//   ilp_inputs_kernel      ILP set-up coefficients over the leaf arrays (query.cpp:1154-1181)
 //   random_*_kernel        measured lookup roofline (random gathers from L2 / HBM)
 //
 // Reference behaviour reproduced: query.cpp:480-527 (scan of every position, both strands),
@@ -29,21 +39,30 @@
 
 #include "flat_index.hpp"
 
+#ifndef CAMMIQ_MIN_BLOCKS
+#define CAMMIQ_MIN_BLOCKS 3
+#endif
+
 namespace cammiq {
 
-static const int kScanThreads = 256;          // 8 warps, each streaming its own 32-read sub-tiles
+static const int kScanThreads = 256;          // 8 warps, each streaming its own 32-read tiles
 static const int kWarpsPerBlock = kScanThreads / 32;
-static const int kQueueCap = 512;             // per-warp candidate queue (drained when > 256 used)
-static const int kHitSeg = 8;                 // per-read hit slots in shared memory
-static const int kHitSpill = 1024;            // per-read overflow in global memory (2 tables x 2 strands x 251)
-static const int kStepUnroll = 4;             // bases per thread between filter tests (8 loads in flight)
+#ifndef CAMMIQ_STRIP
+#define CAMMIQ_STRIP 8
+#endif
+static const int kStrip = CAMMIQ_STRIP;       // read positions per lane and phase-1 round (that many probes in flight per lane)
+static const int kQueueCap = 512;             // per-warp candidate queue; a round adds at most 32 * kStrip
+static const int kHitSeg = 8;                 // per-read hit slots in shared memory (the rest spills to global)
+static const int kLightHits = 16;             // longer hit lists are deduplicated by the whole warp
 static const int kProbeUnroll = 4;            // micro-benchmark unroll
 static const int kMaxBlocksPerSM = 4;
 static const uint32_t kMaxSmemGenomes = 8191; // 2*(G+1) u32 block counters must fit 64 KB
+static const uint32_t kTileSlack = 32;        // bytes readable past a staged tile (unaligned 20-byte windows)
+static const uint32_t kSetEmpty = 0xFFFFFFFFu;
 
 struct ScanParams {
 	// index
-	const TableSlot *table;
+	const TableBucket *table;
 	uint64_t table_mask;
 	const uint2 *filter;      // NULL: no filter, phase 1 probes the table
 	uint32_t filter_words;    // number of 64-bit filter words
@@ -63,14 +82,18 @@ struct ScanParams {
 	uint64_t read_base;       // caller's index of this launch's first read (chunked submission)
 	const uint8_t *lengths;
 	uint64_t n_reads;
-	uint32_t tile_cap;        // bytes of one staging buffer (32 reads); 2 per warp
+	uint32_t tile_cap;        // bytes of a warp's raw staging buffer (32 reads as they arrive)
+	uint32_t words_per_read;  // 32-bit words per read in the warp's packed buffer: ceil(longest/16) + 2, odd
 	// outputs
 	int smem_counters;        // 1: block-private genome counters + partials, 0: global atomics
 	uint32_t *partials;       // [gridDim.x][2*(G+1)]
 	unsigned long long *counts; // [2*(G+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid n_pair_records
 	uint32_t *rcount_u, *rcount_d;
 	unsigned long long *pair_records; // SC: (a<<32|b) per D_PAIR read
-	uint32_t *hit_spill;      // [total warps][32][kHitSpill]
+	uint32_t *hit_spill;      // [total warps][32][spill_stride]
+	uint32_t spill_stride;    // per-read overflow capacity: 4*(longest - h + 1) - kHitSeg hits at most
+	uint32_t *dedup_sets;     // [total warps][dedup_slots] hash-set scratch of the cooperative dedup
+	uint32_t dedup_slots;     // power of two >= 2 * (kHitSeg + spill_stride)
 	unsigned long long *probe_count; // [4]: probes, candidates, leaf hits, chained bucket loads
 	// optional per-read outputs
 	uint8_t *read_class;
@@ -81,20 +104,16 @@ struct ScanParams {
 
 // ------------------------------------------------------------------------------ helpers
 
-// A/a=0 C/c=1 G/g=2 T/t=3 (query.cpp:1860-1883); `bad` is raised for any other byte.
-__device__ __forceinline__ uint32_t decodeBase(uint32_t c, bool &bad) {
-	uint32_t u = (c & 0xDFu) - 0x41u; // fold case; 'A' -> 0, 'C' -> 2, 'G' -> 6, 'T' -> 19
-	bad |= (u > 19u) || !((0x80045u >> u) & 1u);
-	uint32_t t = (c >> 1) & 3u;
-	return t ^ (t >> 1);
-}
-
 // 32 bytes = one sector = one prefix-table bucket, fetched with a single 256-bit load
 // (LDG.E.256 on sm_100a), read-only path, no L1 allocation (every probe is a fresh sector).
-__device__ __forceinline__ void loadBucket(const TableSlot *b, unsigned long long &k0,
-		unsigned long long &r0, unsigned long long &k1, unsigned long long &r1) {
+__device__ __forceinline__ void loadBucket(const TableBucket *b, unsigned long long &k0,
+		unsigned long long &k1, unsigned long long &r0, unsigned long long &r1) {
 	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-		: "=l"(k0), "=l"(r0), "=l"(k1), "=l"(r1) : "l"(b));
+		: "=l"(k0), "=l"(k1), "=l"(r0), "=l"(r1) : "l"(b));
+}
+// the two keys of a bucket alone (first half of the sector): phase 1 without a filter
+__device__ __forceinline__ void loadBucketKeys(const TableBucket *b, unsigned long long &k0, unsigned long long &k1) {
+	asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(b));
 }
 
 // L2 residency is the whole point of the filter: its words are loaded with an evict_last
@@ -102,17 +121,21 @@ __device__ __forceinline__ void loadBucket(const TableSlot *b, unsigned long lon
 // updates, the read tiles) is issued evict_first, so the 64 MB filter is what the L2 keeps.
 __device__ __forceinline__ unsigned long long policyEvictLast() {
 	unsigned long long p;
-	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
 	return p;
 }
 __device__ __forceinline__ unsigned long long policyEvictFirst() {
 	unsigned long long p;
-	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
 	return p;
 }
 __device__ __forceinline__ uint2 loadFilterWord(const uint2 *f, unsigned long long policy) {
 	uint2 v;
+#ifdef CAMMIQ_FILTER_L1_ALLOC
 	asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(f), "l"(policy));
+#else
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(f), "l"(policy));
+#endif
 	return v;
 }
 __device__ __forceinline__ uint32_t loadStreamU32(const uint32_t *a) {
@@ -155,112 +178,73 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
 		"DONE_%=:\n\t}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
 }
 
-struct WarpState {
-	uint32_t hits[32][kHitSeg];    // table<<31 | leaf id, per read of the warp's sub-tile
-	uint16_t queue[kQueueCap];     // slot<<9 | strand<<8 | position
-	uint32_t soff[32];             // byte offset of the slot's read inside the staged sub-tile
-	unsigned long long goff[32];   // its offset in the caller's base buffer (fallback path)
-	uint16_t hit_cnt[32];
-	uint8_t rl[32];
-	uint32_t q_count;
-	uint32_t staged;               // sub-tile is in shared memory (else: read from global)
-	uint64_t bar;                  // mbarrier of the warp's staging buffer
-};
-
-// first base of a slot's read, generic address space (phase 2 / trie descent only)
-__device__ __forceinline__ const uint8_t *slotBases(const ScanParams &p, const WarpState &ws, const uint8_t *buf, uint32_t slot) {
-	return ws.staged ? buf + ws.soff[slot] : p.bases + ws.goff[slot];
-}
-
-// base `j` of strand `strand` of a read (strand 1 = reverse complement, query.cpp:447-450)
-template <bool PACKED>
-__device__ __forceinline__ uint32_t strandBase(const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t j) {
-	const uint32_t at = strand ? rl - 1 - j : j;
-	uint32_t c;
-	if (PACKED) {
-		c = ((uint32_t) s[at >> 2] >> (6u - 2u * (at & 3u))) & 3u;
-	} else {
-		bool bad = false;
-		c = decodeBase(s[at], bad);
-	}
-	return strand ? 3u - c : c;
-}
-
-// Walk the CSR trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).
-template <bool PACKED>
-__device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes,
-		const uint8_t *s, uint32_t rl, uint32_t strand, uint32_t next) {
-	while (ref != kRefNone && !(ref & kRefLeafTag)) {
-		if (next >= rl)
-			return kRefNone;
-		uint32_t code = strandBase<PACKED>(s, rl, strand, next);
-		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
-		next++;
-	}
-	return ref;
-}
-
-__device__ __forceinline__ uint32_t ldsWord(uint32_t addr) {
+__device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
 	uint32_t v;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
 
-// reverse the 32 two-bit groups of x
-__device__ __forceinline__ unsigned long long reverseGroups(unsigned long long x) {
-	x = __brevll(x);
-	return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+// reverse complement of a 2-bit packed h-mer held right-aligned (first base most significant):
+// complement, reverse the 32 two-bit groups, drop the unused groups (query.cpp:447-450 on codes)
+__device__ __forceinline__ unsigned long long revcompKey(unsigned long long x, uint32_t h) {
+	x = __brevll(~x);
+	x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+	return x >> (64 - 2 * h);
 }
 
-// 2-bit packing of bases [j, j+n) of strand `strand` of a read (n <= 32, first base most
-// significant, right-aligned).  The reverse-complement strand's window is the reverse
-// complement of the forward window [rl-j-n, rl-j); staged reads are decoded four bases per
-// 32-bit shared load (the bytes were validated by phase 1).
-template <bool PACKED>
-__device__ __forceinline__ unsigned long long strandWindow(const uint8_t *s, bool in_smem, uint32_t rl, uint32_t strand,
-		uint32_t j, uint32_t n) {
-	const uint32_t i = strand ? rl - j - n : j;
-	unsigned long long hv = 0;
-	if (PACKED) {
-		// the window is bits [2i, 2i+2n) of the read's big-endian bit stream
-		if (in_smem) {
-			// three aligned words cover the <= 9 bytes the window touches (the staging buffer has slack)
-			const uint32_t a = smemAddr(s) + (i >> 2);
-			const uint32_t w0 = __byte_perm(ldsWord(a & ~3u), 0u, 0x0123), w1 = __byte_perm(ldsWord((a & ~3u) + 4u), 0u, 0x0123),
-				w2 = __byte_perm(ldsWord((a & ~3u) + 8u), 0u, 0x0123);
-			const uint32_t sh = (a & 3u) * 8u + 2u * (i & 3u); // 0..30
-			const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
-			hv = (((unsigned long long) hi << 32) | lo) >> (64 - 2 * n);
+struct WarpState {
+	uint32_t hits[32][kHitSeg];    // table<<31 | leaf id, per read of the warp's tile
+	uint16_t queue[kQueueCap];     // slot<<10 | strands<<8 | forward window position
+	uint16_t hit_cnt[32];
+	uint16_t strip_base[34];       // exclusive prefix sum of the reads' strip counts, [32] = total
+	uint8_t rl[32];
+	uint32_t set_cnt[2];           // cooperative dedup: distinct U / D leaves of the read in work
+	uint64_t bar;                  // mbarrier of the warp's raw staging buffer
+};
+
+// base j of a packed read (16 bases per word, first base in the top bits)
+__device__ __forceinline__ uint32_t packedBase(uint32_t pk_addr, uint32_t j) {
+	return (ldsU32(pk_addr + ((j >> 4) << 2)) >> (30u - 2u * (j & 15u))) & 3u;
+}
+
+// the h-mer starting at base i of a packed read: bits [2i, 2i+2h) of the read's bit stream
+__device__ __forceinline__ unsigned long long packedWindow(uint32_t pk_addr, uint32_t i, uint32_t h) {
+	const uint32_t a = pk_addr + ((i >> 4) << 2), sh = 2u * (i & 15u);
+	const uint32_t w0 = ldsU32(a), w1 = ldsU32(a + 4), w2 = ldsU32(a + 8);
+	const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+	return (((unsigned long long) hi << 32) | lo) >> (64 - 2 * h);
+}
+
+// Walk the CSR trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).  The forward
+// strand consumes the bases right of the window, the reverse-complement strand the complemented
+// bases left of it; `next` = first base to consume / one past it.
+template <bool REVERSE>
+__device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes, uint32_t pk_addr, uint32_t rl, uint32_t next) {
+	while (ref != kRefNone && !(ref & kRefLeafTag)) {
+		uint32_t code;
+		if (REVERSE) {
+			if (next == 0)
+				return kRefNone;
+			next--;
+			code = 3u - packedBase(pk_addr, next);
 		} else {
-			for (uint32_t t = 0; t < n; t++)
-				hv = (hv << 2) | (((uint32_t) s[(i + t) >> 2] >> (6u - 2u * ((i + t) & 3u))) & 3u);
+			if (next >= rl)
+				return kRefNone;
+			code = packedBase(pk_addr, next);
+			next++;
 		}
-	} else if (in_smem) {
-		const uint32_t a0 = smemAddr(s) + i;
-		for (uint32_t t = 0; t < n; t += 4) {
-			const uint32_t a = a0 + t;
-			const uint32_t w4 = __funnelshift_r(ldsWord(a & ~3u), ldsWord((a & ~3u) + 4u), (a & 3u) * 8u);
-			const uint32_t t4 = (w4 >> 1) & 0x03030303u;
-			const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-#pragma unroll
-			for (int u = 0; u < 4; u++)
-				if (t + u < n) hv = (hv << 2) | ((code4 >> (8 * u)) & 3u);
-		}
-	} else {
-		bool bad = false;
-		for (uint32_t t = 0; t < n; t++)
-			hv = (hv << 2) | decodeBase(s[i + t], bad);
+		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
 	}
-	return strand ? reverseGroups(~hv) >> (64 - 2 * n) : hv;
+	return ref;
 }
 
 // Leaves under a bucket root reached by one strand of a read go to the read's hit list.
-template <bool PACKED>
-__device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws, uint32_t *warp_spill, const uint8_t *s,
-		uint32_t slot, uint32_t rl, uint32_t strand, uint32_t next, unsigned long long refs, uint32_t &n_leaf_hits) {
+template <bool REVERSE>
+__device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws, uint32_t *warp_spill, uint32_t pk_addr,
+		uint32_t slot, uint32_t rl, uint32_t next, unsigned long long refs, uint32_t &n_leaf_hits) {
 	uint32_t leaf[2];
-	leaf[0] = descend<PACKED>((uint32_t) refs, p.nodes_u, s, rl, strand, next);
-	leaf[1] = descend<PACKED>((uint32_t) (refs >> 32), p.nodes_d, s, rl, strand, next);
+	leaf[0] = descend<REVERSE>((uint32_t) refs, p.nodes_u, pk_addr, rl, next);
+	leaf[1] = descend<REVERSE>((uint32_t) (refs >> 32), p.nodes_d, pk_addr, rl, next);
 #pragma unroll
 	for (int t = 0; t < 2; t++) {
 		if (leaf[t] == kRefNone)
@@ -272,80 +256,69 @@ __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws
 		uint32_t old = atomicAdd(word, (slot & 1u) ? 0x10000u : 1u);
 		uint32_t at = (slot & 1u) ? (old >> 16) : (old & 0xFFFFu);
 		if (at < (uint32_t) kHitSeg) ws.hits[slot][at] = e;
-		else if (at < (uint32_t) (kHitSeg + kHitSpill)) warp_spill[(size_t) slot * kHitSpill + at - kHitSeg] = e;
+		else if (at - kHitSeg < p.spill_stride) warp_spill[(size_t) slot * p.spill_stride + at - kHitSeg] = e;
 	}
 }
 
-// Phase 2: the warp drains its candidate queue.  One candidate per lane: recompute the h-mer,
-// probe the prefix table (HBM), descend, append leaves to the owning read's hit list.
-// FILTER: phase 1 does not look for palindromic h-mers (equal to their own reverse complement);
-// for those the forward candidate also serves the reverse strand here and a reverse candidate
-// (a false positive of the filter's other pattern) is dropped.
-template <bool PACKED, bool FILTER>
-__device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, const uint8_t *buf, uint32_t *warp_spill,
-		int lane, uint32_t &n_leaf_hits, uint32_t &n_chained) {
+// Phase 2: the warp drains its candidate queue.  One candidate per lane: re-extract the h-mer of
+// the window, probe the prefix table (HBM; keys are placed by their canonical h-mer, so both
+// strands of a window share the probe sequence and ONE bucket load serves both), descend, append
+// leaves to the read's hit list.  A palindromic h-mer (its own reverse complement) is found by
+// both strands: the two tags are equal and both descents run.
+__device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, uint32_t pk_warp, uint32_t *warp_spill,
+		int lane, uint32_t nq, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
-	const uint32_t nq = ws.q_count;
 	const uint32_t h = p.h;
 	for (uint32_t base = 0; base < nq; base += 32) {
 		const uint32_t k = base + lane;
 		if (k < nq) {
 			const uint32_t item = ws.queue[k];
-			const uint32_t slot = item >> 9, strand = (item >> 8) & 1u, pos = item & 0xFFu;
-			const uint8_t *s = slotBases(p, ws, buf, slot);
+			const uint32_t slot = item >> 10, i = item & 0xFFu;
+			const uint32_t strands = (item >> 8) & 3u;
+			const uint32_t pk_addr = pk_warp + slot * p.words_per_read * 4u;
 			const uint32_t rl = ws.rl[slot];
-			const unsigned long long hv = strandWindow<PACKED>(s, ws.staged != 0, rl, strand, pos, h);
-			// keys are placed by their canonical h-mer (flat_index.hpp, homeBucketHost)
-			const unsigned long long hv_rc = reverseGroups(~hv) >> (64 - 2 * h);
-			const bool palin = FILTER && hv == hv_rc;
-			if (palin && strand)
-				continue;
-			uint64_t b = mixKey(hv < hv_rc ? hv : hv_rc) & p.table_mask;
-			unsigned long long k0, r0, k1, r1, refs = 0;
-			bool found = false;
+			const unsigned long long hf = packedWindow(pk_addr, i, h), hr = revcompKey(hf, h);
+			const unsigned long long tag_f = hf | kKeyOccupied, tag_r = hr | kKeyOccupied;
+			uint64_t b = mixKey(hf < hr ? hf : hr) & p.table_mask;
+			unsigned long long refs_f = 0, refs_r = 0;
+			bool found_f = !(strands & 1u), found_r = !(strands & 2u); // "nothing left to find" per strand
+			bool hit_f = false, hit_r = false;
 			for (;;) {
-				loadBucket(p.table + 2 * b, k0, r0, k1, r1);
-				if (k0 == hv) { refs = r0; found = true; }
-				else if (k1 == hv) { refs = r1; found = true; }
-				if (found || k0 == kEmptyKey || k1 == kEmptyKey)
+				unsigned long long k0, k1, r0, r1;
+				loadBucket(p.table + b, k0, k1, r0, r1);
+				const unsigned long long k0m = k0 & ~kBucketOverflow;
+				if (!found_f) {
+					if (k0m == tag_f) { refs_f = r0; found_f = hit_f = true; }
+					else if (k1 == tag_f) { refs_f = r1; found_f = hit_f = true; }
+				}
+				if (!found_r) {
+					if (k0m == tag_r) { refs_r = r0; found_r = hit_r = true; }
+					else if (k1 == tag_r) { refs_r = r1; found_r = hit_r = true; }
+				}
+				if ((found_f && found_r) || !(k0 & kBucketOverflow))
 					break;
-				b = (b + 1) & p.table_mask; // full bucket: the key may have spilled to the next one
+				b = (b + 1) & p.table_mask; // a key passed this full bucket: look further
 				n_chained++;
 			}
-			if (found) {
-				collectLeaves<PACKED>(p, ws, warp_spill, s, slot, rl, strand, pos + h, refs, n_leaf_hits);
-				if (palin) // the reverse strand holds the same h-mer at position rl-h-pos
-					collectLeaves<PACKED>(p, ws, warp_spill, s, slot, rl, 1u, rl - pos, refs, n_leaf_hits);
-			}
+			if (hit_f)
+				collectLeaves<false>(p, ws, warp_spill, pk_addr, slot, rl, i + h, refs_f, n_leaf_hits);
+			if (hit_r)
+				collectLeaves<true>(p, ws, warp_spill, pk_addr, slot, rl, i, refs_r, n_leaf_hits);
 		}
 	}
 	__syncwarp();
-	if (lane == 0)
-		ws.q_count = 0;
-	__syncwarp();
-}
-
-__device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {
-	uint32_t v;
-	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-	return v;
-}
-
-__device__ __forceinline__ uint32_t ldsU32(uint32_t addr) {
-	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-	return v;
 }
 
 template <int MODE, bool FILTER, bool PACKED>
-__global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams p) {
-	// [8 warps][tile_cap bytes of ASCII] | [2*(G+1) u32 genome counters]
+__global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_kernel(ScanParams p) {
+	// [8 warps][tile_cap + slack: raw tile] | [8 warps][32 * words_per_read: packed tile] | [2*(G+1) u32 genome counters]
 	extern __shared__ __align__(128) uint8_t dyn_smem[];
 	__shared__ __align__(16) WarpState warp_state[kWarpsPerBlock];
 	__shared__ unsigned long long block_tot[2]; // nundet, nconf
 
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * p.tile_cap);
+	const uint32_t raw_bytes = p.tile_cap + kTileSlack, pk_bytes = 32u * p.words_per_read * 4u;
+	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * (raw_bytes + pk_bytes));
 	const uint32_t G1 = p.n_genomes + 1, ncnt = 2 * G1;
 	if (p.smem_counters)
 		for (uint32_t i = tid; i < ncnt; i += blockDim.x)
@@ -353,38 +326,40 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 	if (tid < 2)
 		block_tot[tid] = 0;
 	WarpState &ws = warp_state[wib];
-	if (lane == 0) {
-		ws.q_count = 0;
+	if (lane == 0)
 		mbarInit(&ws.bar, 1);
-	}
 	__syncthreads();
 
 	const uint32_t h = p.h;
 	const unsigned long long pol_keep = policyEvictLast(), pol_stream = policyEvictFirst();
 	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
 	const uint32_t top_shift = 2 * h - 2;
-	uint8_t *wbuf = dyn_smem + (size_t) wib * p.tile_cap;
-	uint32_t *warp_spill = p.hit_spill + ((size_t) blockIdx.x * kWarpsPerBlock + wib) * 32 * kHitSpill;
-	unsigned long long n_undet = 0, n_conf = 0, n_invalid = 0;
-	uint32_t n_probes = 0, n_cand = 0, n_leaf_hits = 0, n_chained = 0; // per lane
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	uint8_t *raw = dyn_smem + (size_t) wib * raw_bytes;
+	const uint32_t raw_addr = smemAddr(raw);
+	const uint32_t pk_warp = smemAddr(dyn_smem + (size_t) kWarpsPerBlock * raw_bytes + (size_t) wib * pk_bytes);
+	const uint32_t pk_mine = pk_warp + (uint32_t) lane * p.words_per_read * 4u;
+	const size_t warp_global = (size_t) blockIdx.x * kWarpsPerBlock + wib;
+	uint32_t *warp_spill = p.hit_spill + warp_global * 32 * p.spill_stride;
+	uint32_t *warp_set = p.dedup_sets + warp_global * p.dedup_slots;
+	uint32_t n_undet = 0, n_conf = 0, n_invalid = 0, n_probes = 0; // per lane (a lane sees < 2^32 / 512 reads per launch)
+	uint32_t n_cand = 0, n_leaf_hits = 0, n_chained = 0; // n_cand warp-uniform, the others per lane
 	uint32_t parity = 0;
 
-	// Every warp owns sub-tiles of 32 reads (one read per lane) and streams them through its own
-	// staging buffer with its own mbarrier: no block-wide barrier in the loop, the other warps
-	// of the SM cover the (short) bulk-copy latency.
-	const uint64_t n_sub = (p.n_reads + 31) / 32;
-	const uint64_t warp_stride = (uint64_t) gridDim.x * kWarpsPerBlock;
-	uint64_t sub = (uint64_t) blockIdx.x * kWarpsPerBlock + wib;
+	const uint32_t n_sub = (uint32_t) ((p.n_reads + 31) / 32); // the host keeps a launch below 2^32 tiles
+	const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
+	uint32_t sub = blockIdx.x * kWarpsPerBlock + wib;
 
 	struct SubTile {
-		unsigned long long off, start; // this lane's read offset; 16-byte aligned start of the span
+		unsigned long long off; // this lane's read offset in the caller's base buffer
+		uint32_t lead;          // its offset inside the staged span (the span starts 16-byte aligned)
 		uint32_t rl, bytes;
 		bool have, staged;
 	};
-	// offsets / lengths of a sub-tile's reads and the byte span they cover (warp-uniform)
-	auto describe = [&](uint64_t sub_idx) -> SubTile {
+	// offsets / lengths of a tile's reads and the byte span they cover (warp-uniform)
+	auto describe = [&](uint32_t sub_idx) -> SubTile {
 		SubTile t;
-		const uint64_t r = sub_idx * 32 + lane;
+		const uint64_t r = (uint64_t) sub_idx * 32 + lane;
 		t.have = r < p.n_reads;
 		if (PACKED)
 			t.off = t.have ? (p.offsets32 ? (unsigned long long) p.offsets32[r] : p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
@@ -398,169 +373,219 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 			lo = tl < lo ? tl : lo;
 			hi = th > hi ? th : hi;
 		}
-		t.start = lo & ~15ull;
-		t.bytes = hi > t.start ? (uint32_t) min((hi - t.start + 15ull) & ~15ull, 0xFFFFFFF0ull) : 0u;
+		const unsigned long long start = lo & ~15ull;
+		t.bytes = hi > start ? (uint32_t) min((hi - start + 15ull) & ~15ull, 0xFFFFFFF0ull) : 0u;
 		t.staged = t.bytes > 0 && t.bytes <= p.tile_cap; // else: the reads are fetched from global directly
+		t.lead = t.staged && t.have ? (uint32_t) (t.off - start) : 0u;
 		return t;
 	};
-
-	SubTile cur;
-	cur.have = false; cur.staged = false; cur.rl = 0; cur.off = 0; cur.start = 0; cur.bytes = 0;
-	if (sub < n_sub)
-		cur = describe(sub);
-	for (; sub < n_sub; sub += warp_stride) {
-		// one TMA bulk copy brings the sub-tile's ASCII bytes into the warp's buffer
-		if (cur.staged) {
-			if (lane == 0) {
-				mbarExpectTx(&ws.bar, cur.bytes);
-				bulkCopyG2S(wbuf, p.bases + cur.start, cur.bytes, &ws.bar, pol_stream);
-			}
+	// one bulk copy per tile; lane 0's read is the tile's first one only if offsets ascend, so the
+	// span start travels by shuffle from whichever lane holds the lowest offset
+	auto issueCopy = [&](const SubTile &t) {
+		if (!t.staged)
+			return;
+		const unsigned long long start = t.off - t.lead;
+		const uint32_t holders = __ballot_sync(0xffffffffu, t.have);
+		const unsigned long long span = __shfl_sync(0xffffffffu, start, __ffs(holders) - 1);
+		if (lane == 0) {
+			mbarExpectTx(&ws.bar, t.bytes);
+			bulkCopyG2S(raw, p.bases + span, t.bytes, &ws.bar, pol_stream);
 		}
-		// the next sub-tile's offsets / lengths are fetched while this one is in flight
-		SubTile nxt;
-		nxt.have = false; nxt.staged = false; nxt.rl = 0; nxt.off = 0; nxt.start = 0; nxt.bytes = 0;
-		if (sub + warp_stride < n_sub)
-			nxt = describe(sub + warp_stride);
+	};
+
+	if (sub < n_sub)
+		issueCopy(describe(sub));
+	for (; sub < n_sub; sub += warp_stride) {
+		// (the tile's offsets / lengths are re-read rather than carried in registers across a tile)
+		const SubTile cur = describe(sub);
 		if (cur.staged) {
 			mbarWait(&ws.bar, parity);
 			parity ^= 1u;
 		}
-		const uint64_t r = sub * 32 + lane;
+		const uint64_t r = (uint64_t) sub * 32 + lane;
 		const bool have = cur.have, staged = cur.staged;
 		const uint32_t rl = cur.rl;
-		const uint8_t *tbuf = wbuf;
-		const uint32_t soff = staged && have ? (uint32_t) (cur.off - cur.start) : 0u;
-		ws.soff[lane] = soff;
-		ws.goff[lane] = have ? cur.off : 0ull;
-		ws.rl[lane] = (uint8_t) rl;
-		ws.hit_cnt[lane] = 0;
-		if (lane == 0)
-			ws.staged = staged ? 1u : 0u;
-		__syncwarp();
-
-		// ---- phase 1: thread per read, rolling hashes of both strands, filter / table test ------
-		// Four bases per iteration: one (unaligned) 32-bit shared load, SIMD-in-register decode
-		// and validation, then four roll steps; positions with a full h-base window are probed.
-		const uint32_t sbase = smemAddr(tbuf) + soff;
-		const uint8_t *gbase = p.bases + (have ? cur.off : 0ull);
-		uint32_t bad4 = 0;
-		unsigned long long hf = 0, hr = 0;
 		const uint32_t wmax = __reduce_max_sync(0xffffffffu, rl);
-		for (uint32_t j0 = 0; j0 < wmax; j0 += kStepUnroll) {
-			// bytes j0..j0+3 of the read (garbage past rl is masked below)
-			uint32_t w4 = 0;
-			if (PACKED) {
-				// one byte = the four codes of this iteration (validated and zero-padded by the host)
-				if (j0 < rl)
-					w4 = staged ? ldsU8(sbase + (j0 >> 2)) : (uint32_t) gbase[j0 >> 2];
-			} else if (j0 < rl) {
-				if (staged) {
-					const uint32_t a = sbase + j0;
-					w4 = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
-				} else {
-#pragma unroll
-					for (int u = 0; u < kStepUnroll; u++)
-						if (j0 + u < rl) w4 |= (uint32_t) gbase[j0 + u] << (8 * u);
-				}
-			}
-			// codes: A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
-			// letter the code stands for (one byte permute)
-			uint32_t code4;
-			if (PACKED) {
-				code4 = w4;
-			} else {
-				const uint32_t t4 = (w4 >> 1) & 0x03030303u;
-				code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-				const uint32_t nib = code4 | (code4 >> 4);
-				const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-				const uint32_t left = rl > j0 ? rl - j0 : 0u;
-				const uint32_t live = left >= 4u ? 0xFFFFFFFFu : ((1u << (8u * left)) - 1u);
-				bad4 |= ((w4 & 0xDFDFDFDFu) ^ expect4) & live;
-			}
 
-			uint2 ff[kStepUnroll];                                // FILTER: filter words
-			uint32_t bsel[kStepUnroll];
-			unsigned long long kf[kStepUnroll];                   // !FILTER: the forward key and the strands' shared bucket
-			unsigned long long bk[kStepUnroll][4];
-#pragma unroll
-			for (int u = 0; u < kStepUnroll; u++) {
-				const uint32_t j = j0 + u;
-				const uint32_t c = PACKED ? (code4 >> (6 - 2 * u)) & 3u : (code4 >> (8 * u)) & 3u;
-				hf = ((hf << 2) | c) & kmask;
-				hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);
-				if (j + 1 >= h && j < rl) {
-					if (FILTER) {
-						// hr is the reverse complement of the window hf covers: ONE probe with the
-						// canonical h-mer answers both strands
-						uint32_t a;
-						const bool fwd_is_canon = hf <= hr;
-						filterHash(fwd_is_canon ? hf : hr, a, bsel[u]);
-						// bit 31 of B is unused by the selectors: remember the orientation
-						bsel[u] = (bsel[u] & 0x7FFFFFFFu) | (fwd_is_canon ? 0x80000000u : 0u);
-						ff[u] = loadFilterWord(p.filter + filterWordIndex(a, p.filter_words), pol_keep);
-					} else {
-						kf[u] = hf;
-						// a key and its reverse complement share their home bucket: one sector per position
-						loadBucket(p.table + 2 * (mixKey(hf < hr ? hf : hr) & p.table_mask), bk[u][0], bk[u][1], bk[u][2], bk[u][3]);
-					}
-				}
-			}
-			if (j0 + kStepUnroll >= h) { // warp-uniform: some step of this iteration has a full window
-#pragma unroll
-				for (int u = 0; u < kStepUnroll; u++) {
-					const uint32_t j = j0 + u;
-					bool cand_f = false, cand_r = false;
-					if (j + 1 >= h && j < rl) {
-						if (FILTER) {
-							// pattern of B: the canonical orientation is a key; other pattern: its reverse
-							// complement is.  fwd_canon says which strand holds the canonical orientation.
-							const bool same = filterTest(ff[u].x, ff[u].y, bsel[u]);
-							const bool other = filterTest(ff[u].x, ff[u].y, filterOtherPattern(bsel[u]));
-							// (a palindromic h-mer is its own reverse complement: phase 2 serves its reverse
-							// strand from the forward candidate)
-							const bool fwd_canon = (bsel[u] & 0x80000000u) != 0;
-							cand_f = fwd_canon ? same : other;
-							cand_r = fwd_canon ? other : same;
+		// ---- stage: lane r packs read r, 16 bases per word, first base in the top bits -------------
+		uint32_t bad = 0;
+		{
+			const uint32_t src = raw_addr + cur.lead;
+			const uint8_t *gsrc = p.bases + (have ? cur.off : 0ull);
+			const uint32_t n_words = (wmax + 15u) >> 4;
+			for (uint32_t c = 0; c < n_words; c++) {
+				const int n = (int) rl - (int) (16u * c); // bases of this read in word c
+				uint32_t word = 0;
+				if (n > 0) {
+					if (PACKED) {
+						// four bytes of the host-packed read = this word, big-endian (validated by the host)
+						uint32_t v = 0;
+						if (staged) {
+							const uint32_t a = src + 4u * c;
+							v = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
 						} else {
-							// candidate = the bucket holds the key, or is full and the key may have spilled
-							// the reverse strand's key is recomputed rather than kept live across the loads
-							const unsigned long long kr = reverseGroups(~kf[u]) >> (64 - 2 * h);
-							const bool full = bk[u][0] != kEmptyKey && bk[u][2] != kEmptyKey;
-							cand_f = bk[u][0] == kf[u] || bk[u][2] == kf[u] || full;
-							cand_r = bk[u][0] == kr || bk[u][2] == kr || full;
+							const uint32_t nb = min(4u, ((uint32_t) n + 3u) >> 2);
+							for (uint32_t t = 0; t < nb; t++)
+								v |= (uint32_t) gsrc[4u * c + t] << (8u * t);
+						}
+						word = __byte_perm(v, 0u, 0x0123);
+					} else {
+						uint32_t d[4] = {0u, 0u, 0u, 0u};
+						if (staged) {
+							const uint32_t a = src + 16u * c, al = a & ~3u, sh = (a & 3u) * 8u;
+							uint32_t w[5];
+#pragma unroll
+							for (int t = 0; t < 5; t++)
+								w[t] = ldsU32(al + 4u * t);
+#pragma unroll
+							for (int t = 0; t < 4; t++)
+								d[t] = __funnelshift_r(w[t], w[t + 1], sh);
+						} else {
+							const uint32_t nb = min(16u, (uint32_t) n);
+							for (uint32_t t = 0; t < nb; t++)
+								d[t >> 2] |= (uint32_t) gsrc[16u * c + t] << (8u * (t & 3u));
+						}
+#pragma unroll
+						for (int t = 0; t < 4; t++) {
+							// codes A/a=0 C/c=1 G/g=2 T/t=3 (query.cpp:1860-1883) in each byte; validity: fold
+							// case and compare with the letter each code stands for (one byte permute)
+							const uint32_t t4 = (d[t] >> 1) & 0x03030303u;
+							const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+							const uint32_t nib = code4 | (code4 >> 4);
+							const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+							const int left = n - 4 * t;
+							const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
+							bad |= ((d[t] & 0xDFDFDFDFu) ^ expect4) & live;
+							// four 2-bit codes -> one byte, first base in the top bits
+							word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
 						}
 					}
-					if (cand_f | cand_r) { // rare: one branch on the common path
-						if (cand_f) {
-							// forward strand, position i = j-h+1
-							uint32_t at = atomicAdd(&ws.q_count, 1u);
-							ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | (j + 1 - h));
-							n_cand++;
-						}
-						if (cand_r) {
-							// reverse-complement strand: this window is rc position rl-1-j
-							uint32_t at = atomicAdd(&ws.q_count, 1u);
-							ws.queue[at] = (uint16_t) (((uint32_t) lane << 9) | 0x100u | (rl - 1 - j));
-							n_cand++;
-						}
-					}
+					if (n < 16)
+						word &= 0xFFFFFFFFu << (32 - 2 * n);
 				}
-				__syncwarp();
-				// at most 2*kStepUnroll*32 = 256 candidates arrive per iteration: drain above half
-				if (ws.q_count > (uint32_t) (kQueueCap - 2 * kStepUnroll * 32))
-					drainQueue<PACKED, FILTER>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+				asm volatile("st.shared.u32 [%0], %1;" ::"r"(pk_mine + 4u * c), "r"(word) : "memory");
 			}
 		}
-		const bool bad = bad4 != 0;
-		if (have && rl >= h)
-			n_probes += 2 * (rl - h + 1); // both strands of every window
-		drainQueue<PACKED, FILTER>(p, ws, tbuf, warp_spill, lane, n_leaf_hits, n_chained);
+		const bool valid = have && bad == 0 && rl >= h;
+		const uint32_t npos = valid ? rl - h + 1 : 0;
+		// strips of the tile, flattened over its reads
+		const uint32_t my_strips = (npos + kStrip - 1) / kStrip;
+		uint32_t incl = my_strips;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += up;
+		}
+		ws.strip_base[lane] = (uint16_t) (incl - my_strips);
+		if (lane == 31)
+			ws.strip_base[32] = (uint16_t) incl;
+		ws.rl[lane] = (uint8_t) rl;
+		ws.hit_cnt[lane] = 0;
+		const uint32_t total_strips = __shfl_sync(0xffffffffu, incl, 31);
+		const uint32_t first_strips = __shfl_sync(0xffffffffu, my_strips, 0);
+		const bool uniform_strips = __all_sync(0xffffffffu, my_strips == first_strips) && first_strips > 0;
+		const uint32_t strip_inv = uniform_strips ? (65536u + my_strips - 1) / my_strips : 0u;
+		n_probes += 2 * npos; // both strands of every window
+		__syncwarp();
+		// the raw buffer is free: the next tile's bytes arrive while this one is scanned
+		if (sub + warp_stride < n_sub)
+			issueCopy(describe(sub + warp_stride));
 
-		// ---- phase 3: thread per read: leaf set -> decision (query.cpp:529-636) ------------------
+		// ---- phase 1: a strip of kStrip positions per lane, all probes in flight before any test ---
+		uint32_t nq = 0; // queue fill, warp-uniform
+		for (uint32_t k0 = 0; k0 < total_strips; k0 += 32) {
+			const uint32_t k = k0 + lane;
+			const bool live = k < total_strips;
+			// the read this strip belongs to: a division when all reads of the tile have the same
+			// number of strips (the usual case), else the last read whose first strip is <= k
+			uint32_t slot = 0, i0 = 0;
+			if (uniform_strips) {
+				slot = (k * strip_inv) >> 16; // exact: k < 2^10, strips per read <= 32
+				i0 = (k - slot * my_strips) * kStrip;
+				if (!live) slot = 0, i0 = 0;
+			} else {
+#pragma unroll
+				for (int step = 16; step > 0; step >>= 1)
+					if (ws.strip_base[slot + step] <= k) slot += step;
+				i0 = live ? (k - ws.strip_base[slot]) * kStrip : 0u;
+			}
+			const uint32_t s_rl = ws.rl[slot];
+			const uint32_t count = live ? min((uint32_t) kStrip, s_rl - h + 1 - i0) : 0u;
+			// bases i0 .. i0+h+kStrip-2 of the read lie in three packed words (i0 is a multiple of kStrip)
+			static_assert(kStrip == 4 || kStrip == 8, "strips must not straddle the three-word window");
+			const uint32_t a = pk_warp + slot * p.words_per_read * 4u + ((i0 >> 4) << 2), sh = (i0 & 15u) * 2u;
+			const uint32_t w0 = ldsU32(a), w1 = ldsU32(a + 4), w2 = ldsU32(a + 8);
+			const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh), lo2 = w2 << sh;
+			unsigned long long hf = (((unsigned long long) hi << 32) | lo) >> (64 - 2 * h);
+			unsigned long long hr = revcompKey(hf, h);
+			// the bases that enter the window at the strip's later positions, first one in the top bits
+			const uint32_t enter = 2 * h >= 32 ? __funnelshift_l(lo2, lo, 2 * h - 32) : __funnelshift_l(lo, hi, 2 * h);
+
+			uint2 ff[kStrip];                     // FILTER: filter words
+			uint32_t bsel[kStrip];
+			unsigned long long kf[kStrip];        // !FILTER: forward key, the two keys of the strands' shared bucket
+			unsigned long long bk0[kStrip], bk1[kStrip];
+#pragma unroll
+			for (int t = 0; t < kStrip; t++) {
+				if (t > 0) {
+					const uint32_t c = (enter >> (32 - 2 * t)) & 3u;
+					hf = ((hf << 2) | c) & kmask;                                     // query.cpp:493-494
+					hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);    // the window's reverse complement
+				}
+				if (FILTER) {
+					// hr is the reverse complement of the window hf covers: ONE probe with the canonical
+					// h-mer answers both strands
+					uint32_t A;
+					filterHash(hf <= hr ? hf : hr, A, bsel[t]);
+					ff[t] = make_uint2(0u, 0u);
+					if ((uint32_t) t < count)
+						ff[t] = loadFilterWord(p.filter + filterWordIndex(A, p.filter_words), pol_keep);
+				} else {
+					kf[t] = hf;
+					bk0[t] = bk1[t] = 0ull;
+					// a key and its reverse complement share their home bucket: one sector per position
+					if ((uint32_t) t < count)
+						loadBucketKeys(p.table + (mixKey(hf < hr ? hf : hr) & p.table_mask), bk0[t], bk1[t]);
+				}
+			}
+#pragma unroll
+			for (int t = 0; t < kStrip; t++) {
+				bool cand_f, cand_r;
+				if (FILTER) {
+					// the canonical h-mer of the window may be a key, in either orientation: phase 2 looks
+					// for both.  An all-zero word (position past the strip's end) fails the test.
+					cand_f = cand_r = filterTest(ff[t].x, ff[t].y, bsel[t]);
+				} else {
+					// candidate = the bucket holds the key, or a key spilled past this bucket; the reverse
+					// strand's key is recomputed rather than kept live across the loads
+					const unsigned long long tag_f = kf[t] | kKeyOccupied, tag_r = revcompKey(kf[t], h) | kKeyOccupied;
+					const unsigned long long k0m = bk0[t] & ~kBucketOverflow;
+					const bool over = (bk0[t] & kBucketOverflow) != 0;
+					cand_f = k0m == tag_f || bk1[t] == tag_f || over;
+					cand_r = k0m == tag_r || bk1[t] == tag_r || over;
+				}
+				const uint32_t strands = (cand_f ? 1u : 0u) | (cand_r ? 2u : 0u);
+				const uint32_t m = __ballot_sync(0xffffffffu, strands != 0);
+				if (m) { // warp-uniform; the queue slot of a lane is its rank among the lanes with a candidate
+					if (strands)
+						ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) ((slot << 10) | (strands << 8) | (i0 + t));
+					nq += __popc(m);
+				}
+			}
+			// a round adds at most 32 * kStrip entries: drain above half
+			if (nq > (uint32_t) (kQueueCap - 32 * kStrip)) {
+				n_cand += nq;
+				drainQueue(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+				nq = 0;
+			}
+		}
+		n_cand += nq;
+		drainQueue(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+
+		// ---- phase 3: lane r: leaf set of read r -> decision (query.cpp:529-636) -------------------
 		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;
-		const bool valid = have && !bad && rl >= h;
-		const uint32_t nh = valid ? min((uint32_t) ws.hit_cnt[lane], (uint32_t) (kHitSeg + kHitSpill)) : 0;
-		const uint32_t *my_spill = warp_spill + (size_t) lane * kHitSpill;
+		const uint32_t nh = valid ? min((uint32_t) ws.hit_cnt[lane], (uint32_t) kHitSeg + p.spill_stride) : 0;
+		const uint32_t *my_spill = warp_spill + (size_t) lane * p.spill_stride;
 		if (nh > 0) {
 			uint32_t min_r = 0xFFFFFFFFu, max_r = 0;
 			unsigned long long min_p = ~0ull, max_p = 0;
@@ -613,52 +638,116 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 					else cls = CQ_CLASS_CONFLICT;
 				}
 			}
-			// distinct leaves: rcount += 1 per distinct leaf of an accepted read (query.cpp:550-551)
-			const bool accepted = cls >= CQ_CLASS_U;
-			const bool want_sets = p.read_nleaf_u != NULL;
-			if ((MODE == CQ_MODE_P && accepted) || want_sets) {
-				for (uint32_t i = 0; i < nh; i++) {
-					uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
-					bool first = true;
-					for (uint32_t q = 0; q < i && first; q++)
-						first = (q < (uint32_t) kHitSeg ? ws.hits[lane][q] : my_spill[q - kHitSeg]) != e;
-					if (!first)
-						continue;
+		}
+		// distinct leaves: rcount += 1 per distinct leaf of an accepted read (query.cpp:550-551; the
+		// reference collects leaf pointers in a std::set, so a leaf hit at several positions counts once)
+		const bool accepted = cls >= CQ_CLASS_U;
+		const bool want_sets = p.read_nleaf_u != NULL;
+		const bool count_leaves = nh > 0 && ((MODE == CQ_MODE_P && accepted) || want_sets);
+		if (count_leaves && nh <= (uint32_t) kLightHits) {
+			for (uint32_t i = 0; i < nh; i++) {
+				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
+				bool first = true;
+				for (uint32_t q = 0; q < i && first; q++)
+					first = (q < (uint32_t) kHitSeg ? ws.hits[lane][q] : my_spill[q - kHitSeg]) != e;
+				if (!first)
+					continue;
+				const bool is_d = (e & kRefLeafTag) != 0;
+				const uint32_t leaf = e & ~kRefLeafTag;
+				if (MODE == CQ_MODE_P && accepted)
+					redAddStream(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], pol_stream);
+				if (want_sets) {
+					uint32_t at = is_d ? distinct_d : distinct_u;
+					if (at < p.leaf_cap)
+						(is_d ? p.read_leaf_d : p.read_leaf_u)[r * p.leaf_cap + at] = leaf;
+				}
+				if (is_d) distinct_d++;
+				else distinct_u++;
+			}
+		}
+		// long hit lists (near-duplicate strains, dense indices): the whole warp deduplicates one
+		// read at a time through a hash set in global scratch -- linear instead of quadratic work
+		uint32_t heavy = __ballot_sync(0xffffffffu, count_leaves && nh > (uint32_t) kLightHits);
+		while (heavy) {
+			const int src = __ffs(heavy) - 1;
+			heavy &= heavy - 1;
+			const uint32_t s_nh = __shfl_sync(0xffffffffu, nh, src);
+			const bool s_acc = __shfl_sync(0xffffffffu, (MODE == CQ_MODE_P && accepted) ? 1 : 0, src) != 0;
+			const uint64_t s_r = (uint64_t) sub * 32 + src;
+			const uint32_t set_mask = p.dedup_slots - 1;
+			for (uint32_t q = lane; q < p.dedup_slots; q += 32)
+				warp_set[q] = kSetEmpty;
+			if (lane < 2)
+				ws.set_cnt[lane] = 0;
+			__syncwarp();
+			const uint32_t *s_spill = warp_spill + (size_t) src * p.spill_stride;
+			for (uint32_t i = lane; i < s_nh; i += 32) {
+				const uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[src][i] : s_spill[i - kHitSeg];
+				uint32_t q = (e * 0x9E3779B1u) >> 7 & set_mask;
+				bool first;
+				for (;;) {
+					const uint32_t seen = atomicCAS(&warp_set[q], kSetEmpty, e);
+					if (seen == kSetEmpty || seen == e) {
+						first = seen == kSetEmpty;
+						break;
+					}
+					q = (q + 1) & set_mask;
+				}
+				if (first) {
 					const bool is_d = (e & kRefLeafTag) != 0;
 					const uint32_t leaf = e & ~kRefLeafTag;
-					if (MODE == CQ_MODE_P && accepted)
+					if (s_acc)
 						redAddStream(is_d ? &p.rcount_d[leaf] : &p.rcount_u[leaf], pol_stream);
-					if (want_sets) {
-						uint32_t at = is_d ? distinct_d : distinct_u;
-						if (at < p.leaf_cap)
-							(is_d ? p.read_leaf_d : p.read_leaf_u)[r * p.leaf_cap + at] = leaf;
-					}
-					if (is_d) distinct_d++;
-					else distinct_u++;
+					const uint32_t at = atomicAdd(&ws.set_cnt[is_d ? 1 : 0], 1u);
+					if (want_sets && at < p.leaf_cap)
+						(is_d ? p.read_leaf_d : p.read_leaf_u)[s_r * p.leaf_cap + at] = leaf;
 				}
 			}
+			__syncwarp();
+			if (lane == src) {
+				distinct_u = ws.set_cnt[0];
+				distinct_d = ws.set_cnt[1];
+			}
+			__syncwarp();
 		}
 
 		// ---- counters (the effects of query.cpp:542-636) ---------------------------------------------
+		const bool inc_u = have && (cls == CQ_CLASS_U || cls == CQ_CLASS_UD || (cls == CQ_CLASS_D_INTER && MODE == CQ_MODE_SC));
+		const bool inc_d = have && cls >= CQ_CLASS_D_PAIR;
+		const bool inc_b = have && cls == CQ_CLASS_D_PAIR;
 		if (have) {
-			const bool inc_u = cls == CQ_CLASS_U || cls == CQ_CLASS_UD || (cls == CQ_CLASS_D_INTER && MODE == CQ_MODE_SC);
-			const bool inc_d = cls >= CQ_CLASS_D_PAIR;
 			if (!valid) n_invalid++;
 			if (cls == CQ_CLASS_UNLABELED) n_undet++;
 			else if (cls == CQ_CLASS_CONFLICT) n_conf++;
-			else if (p.smem_counters) {
-				if (inc_u) atomicAdd(&smem_counts[rid_a], 1u);
-				if (inc_d) atomicAdd(&smem_counts[G1 + rid_a], 1u);
-				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&smem_counts[G1 + rid_b], 1u);
-			} else {
-				if (inc_u) atomicAdd(&p.counts[rid_a], 1ull);
-				if (inc_d) atomicAdd(&p.counts[G1 + rid_a], 1ull);
-				if (cls == CQ_CLASS_D_PAIR) atomicAdd(&p.counts[G1 + rid_b], 1ull);
+		}
+		// lanes that bump the same genome combine first (match_any): one add per distinct genome
+		// and warp, however skewed the sample is
+#pragma unroll
+		for (int which = 0; which < 3; which++) {
+			const bool inc = which == 0 ? inc_u : which == 1 ? inc_d : inc_b;
+			const uint32_t at = (which == 0 ? 0u : G1) + (which == 2 ? rid_b : rid_a);
+			const uint32_t m = __ballot_sync(0xffffffffu, inc);
+			if (inc) {
+				const uint32_t peers = __match_any_sync(m, at);
+				if (lane == __ffs(peers) - 1) {
+					if (p.smem_counters) atomicAdd(&smem_counts[at], (uint32_t) __popc(peers));
+					else atomicAdd(&p.counts[at], (unsigned long long) __popc(peers));
+				}
 			}
-			if (MODE == CQ_MODE_SC && cls == CQ_CLASS_D_PAIR) {
-				unsigned long long at = atomicAdd(&p.counts[2 * G1 + 3], 1ull);
-				p.pair_records[at] = ((unsigned long long) rid_a << 32) | rid_b;
+		}
+		if (MODE == CQ_MODE_SC) {
+			// one pair record per D_PAIR read; the warp reserves its records with one atomic
+			const uint32_t m = __ballot_sync(0xffffffffu, inc_b);
+			if (m) {
+				unsigned long long base = 0;
+				if (lane == __ffs(m) - 1)
+					base = atomicAdd(&p.counts[2 * G1 + 3], (unsigned long long) __popc(m));
+				base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+				if (inc_b)
+					p.pair_records[base + __popc(m & lt_mask)] = ((unsigned long long) rid_a << 32) | rid_b;
 			}
+		}
+		if (have) {
 			if (p.read_class) {
 				p.read_class[r] = (uint8_t) cls;
 				p.read_rid_a[r] = rid_a;
@@ -669,31 +758,27 @@ __global__ void __launch_bounds__(kScanThreads, 3) scan_reads_kernel(ScanParams 
 				p.read_nleaf_d[r] = distinct_d;
 			}
 		}
-		__syncwarp(); // every lane is done with this staging buffer and the warp state
-		cur = nxt;
+		__syncwarp(); // every lane is done with the packed tile and the warp state
 	}
 
 	// ---- block totals ---------------------------------------------------------------------------------
+	unsigned long long undet64 = n_undet, conf64 = n_conf, invalid64 = n_invalid, probes64 = n_probes, leaf64 = n_leaf_hits,
+		chain64 = n_chained;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
-		n_undet += __shfl_xor_sync(0xffffffffu, n_undet, o);
-		n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
-		n_invalid += __shfl_xor_sync(0xffffffffu, n_invalid, o);
-	}
-	unsigned long long probes64 = n_probes, cand64 = n_cand, leaf64 = n_leaf_hits, chain64 = n_chained;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
+		undet64 += __shfl_xor_sync(0xffffffffu, undet64, o);
+		conf64 += __shfl_xor_sync(0xffffffffu, conf64, o);
+		invalid64 += __shfl_xor_sync(0xffffffffu, invalid64, o);
 		probes64 += __shfl_xor_sync(0xffffffffu, probes64, o);
-		cand64 += __shfl_xor_sync(0xffffffffu, cand64, o);
 		leaf64 += __shfl_xor_sync(0xffffffffu, leaf64, o);
 		chain64 += __shfl_xor_sync(0xffffffffu, chain64, o);
 	}
 	if (lane == 0) {
-		if (n_undet) atomicAdd(&block_tot[0], n_undet);
-		if (n_conf) atomicAdd(&block_tot[1], n_conf);
-		if (n_invalid) atomicAdd(&p.counts[ncnt + 2], n_invalid);
+		if (undet64) atomicAdd(&block_tot[0], undet64);
+		if (conf64) atomicAdd(&block_tot[1], conf64);
+		if (invalid64) atomicAdd(&p.counts[ncnt + 2], invalid64);
 		if (probes64) atomicAdd(&p.probe_count[0], probes64);
-		if (cand64) atomicAdd(&p.probe_count[1], cand64);
+		if (n_cand) atomicAdd(&p.probe_count[1], (unsigned long long) n_cand);
 		if (leaf64) atomicAdd(&p.probe_count[2], leaf64);
 		if (chain64) atomicAdd(&p.probe_count[3], chain64);
 	}
@@ -768,9 +853,59 @@ __global__ void __launch_bounds__(256) compact_pairs_kernel(const PairSlot *__re
 	out[atomicAdd(n_out, 1ull)] = table[i];
 }
 
+// ------------------------------------------------------------------- ILP input assembly (8f.3)
+//
+// What runILP_* computes per leaf before it builds the model (query.cpp:1154-1181, 1508-1535):
+//   U leaf l of genome i:  wcov  = ucount1 * (rl - depth) * 1.0 / rl * pow(1 - erate, depth)
+//   D leaf l of (i, j):    wcov1 / wcov2 likewise from ucount1 / ucount2
+// with rl a uint32_t (so ucount * (rl - depth) is 32-bit unsigned arithmetic, kept as such), and
+// per genome the sum of its coverages over map_sp[i] -- the coefficient of COV[i] in the
+// constraints EXP1 / EXP2 (query.cpp:1196-1230) -- and the sum of its leaves' rcount.  One thread
+// per leaf; the per-genome sums are double-precision atomics, so their last bits depend on the
+// order of addition (the reference sums in map_sp order) and pow() is CUDA's, not glibc's:
+// callers compare with a relative tolerance.
+struct IlpParams {
+	const uint32_t *ref1, *ref2;   // genome ids of leaf l at [l * ref_stride] (ref2 = NULL for the unique table)
+	uint32_t ref_stride;
+	const uint16_t *ucount1, *ucount2;
+	const uint8_t *depth;
+	const uint32_t *rcount;        // [n] pleafNode::rcount
+	uint64_t n;
+	uint32_t n_genomes;
+	uint32_t rl;
+	double one_minus_e;
+	double *wcov1, *wcov2;         // [n] out (wcov2 = NULL for the unique table)
+	double *genome_wcov;           // [G+1] out, += coverage of the genome's leaves
+	unsigned long long *genome_rcount; // [G+1] out, += rcount of the genome's leaves
+};
+
+__global__ void __launch_bounds__(256) ilp_inputs_kernel(IlpParams q) {
+	const uint64_t l = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= q.n)
+		return;
+	const uint32_t depth = q.depth[l];
+	const double decay = pow(q.one_minus_e, (double) depth);
+	const double w1 = (double) ((uint32_t) q.ucount1[l] * (q.rl - depth)) * 1.0 / (double) q.rl * decay;
+	q.wcov1[l] = w1;
+	const uint32_t a = q.ref1[l * q.ref_stride], rc = q.rcount[l];
+	if (a >= 1 && a <= q.n_genomes) {
+		atomicAdd(&q.genome_wcov[a], w1);
+		if (rc) atomicAdd(&q.genome_rcount[a], (unsigned long long) rc);
+	}
+	if (q.ref2 != NULL) {
+		const double w2 = (double) ((uint32_t) q.ucount2[l] * (q.rl - depth)) * 1.0 / (double) q.rl * decay;
+		q.wcov2[l] = w2;
+		const uint32_t b = q.ref2[l * q.ref_stride];
+		if (b >= 1 && b <= q.n_genomes) {
+			atomicAdd(&q.genome_wcov[b], w2);
+			if (rc) atomicAdd(&q.genome_rcount[b], (unsigned long long) rc);
+		}
+	}
+}
+
 // ------------------------------------------------------------------- lookup roofline probes
 
-__global__ void __launch_bounds__(256) random_sector_kernel(const TableSlot *table, uint64_t mask,
+__global__ void __launch_bounds__(256) random_sector_kernel(const TableBucket *table, uint64_t mask,
 		uint64_t n_probes, uint64_t seed, unsigned long long *sink) {
 	const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	const uint64_t n_threads = (uint64_t) gridDim.x * blockDim.x;
@@ -781,7 +916,7 @@ __global__ void __launch_bounds__(256) random_sector_kernel(const TableSlot *tab
 		for (int u = 0; u < kProbeUnroll; u++) {
 			uint64_t j = i + (uint64_t) u * n_threads;
 			if (j < n_probes)
-				loadBucket(table + 2 * (mixKey(j + seed) & mask), k0[u], r0[u], k1[u], r1[u]);
+				loadBucket(table + (mixKey(j + seed) & mask), k0[u], r0[u], k1[u], r1[u]);
 		}
 #pragma unroll
 		for (int u = 0; u < kProbeUnroll; u++) {

@@ -18,6 +18,12 @@
  *   cq_ctx_set_host_packing           (ASCII `reads` vector -> 2-bit codes before PCIe)
  *   cq_reset                          resetCounters / resetCounters_sc        query.cpp:1820-1858
  *   cq_get_timing                     the "Time for query" bracket            query.cpp:645-647
+ *   cq_multi_*                        the same calls over the GPUs of one box: reads sharded,
+ *                                     index replicated, ONE NCCL sum-reduce of the counters
+ *                                     (the reference's own data
+ *                                     parallelism is the OpenMP loop of query64mt_p, query.cpp:664)
+ *   cq_ilp_inputs                     ILP set-up coefficients over the leaf arrays
+ *                                     (runILP_*: query.cpp:1154-1181, 1508-1535)
  *
  * All functions return 0 on success and a negative CQ_E* code on failure;
  * cq_last_error() then holds a message for the calling thread.  No exceptions cross the
@@ -34,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CQ_ABI_VERSION 2
+#define CQ_ABI_VERSION 3
 
 enum {
 	CQ_OK = 0,
@@ -242,6 +248,67 @@ int cq_reset(cq_ctx *ctx);
    asynchronously (and overlap the scan) only from pinned memory. */
 int cq_host_alloc(size_t bytes, void **out);
 void cq_host_free(void *p);
+
+/* --------------------------------------------------- several GPUs of one box (8b / 8e) -- */
+/*
+ * cq_multi is cq_ctx over n devices: the index is replicated (cq_multi_upload), cq_multi_query
+ * cuts the reads into n contiguous shards of (nearly) equal base counts, one host thread per device
+ * runs the ordinary pipeline on its shard, and ONE grouped NCCL sum-reduce brings the counter
+ * block (and, in CQ_MODE_P, the per-leaf rcount arrays) to device 0 and from there to `out`.
+ * On return `out` holds the totals over all devices, exactly as cq_query would have produced
+ * them on one (integer sums: independent of n).  Counters accumulate across calls until
+ * cq_multi_reset, like cq_query's.  Per-read outputs are written by each device into its slice of
+ * the caller's buffers.  devices = NULL selects ordinals 0..n_gpus-1.
+ * NCCL is loaded at run time (libnccl.so.2; a copy the process already holds, e.g. torch's, is
+ * reused); with n_gpus = 1 no NCCL is needed.  Not thread-safe; one cq_multi per process is the
+ * intended use (it owns one host thread per device while a query runs).
+ */
+typedef struct cq_multi cq_multi;
+int cq_multi_create(int n_gpus, const int *devices, cq_multi **out);
+void cq_multi_destroy(cq_multi *m);
+int cq_multi_n_gpus(const cq_multi *m);
+int cq_multi_upload(cq_multi *m, const cq_index *idx, uint32_t n_genomes);
+int cq_multi_query(cq_multi *m, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out);
+int cq_multi_query_packed(cq_multi *m, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads, cq_result *out);
+int cq_multi_reset(cq_multi *m);
+/* The i-th device's context (owned by m): host-packing setting, timing, device info. */
+int cq_multi_ctx(cq_multi *m, int i, cq_ctx **out);
+typedef struct {
+	int n_gpus;
+	int nccl_version;        /* ncclGetVersion of the library in use, 0 when n_gpus = 1 */
+	int devices[8];
+	uint64_t shard_reads[8]; /* reads each device scanned in the last query */
+	double reduce_ms;        /* CUDA-event time of the last NCCL reduce on device 0 */
+} cq_multi_info;
+int cq_multi_get_info(const cq_multi *m, cq_multi_info *out);
+
+/* ----------------------------------------------------- ILP input assembly (8f.3) -- */
+/*
+ * What runILP_cplex / runILP_gurobi derive from the scan before they build the model
+ * (query.cpp:1154-1181, 1196-1230; 1508-1535): per leaf
+ *     wcov = ucount * (rl - depth) * 1.0 / rl * pow(1 - erate, depth)
+ * (rl = the uint32_t average read length of query.cpp:1087, so ucount * (rl - depth) is 32-bit
+ * unsigned arithmetic as in the reference), per genome the sum of its leaves' coverages over
+ * Hash::map_sp[g] (the coefficient of COV[g] in the constraints EXP1 / EXP2) and the sum of
+ * their rcount.  Computed on the device from the context's accumulated rcount arrays, one thread
+ * per leaf; leaf order = file order (cq_index_leaves, cq_index_map_sp).  Any output may be NULL.
+ * Per-leaf values agree with the host formula to the last bits of pow(); the per-genome sums are
+ * accumulated with atomics (compare with a relative tolerance, 1e-12 is ample).
+ */
+typedef struct {
+	double erate;           /* -e (the float the reference holds, widened) */
+	uint32_t read_length;   /* rl */
+	double *wcov_u;         /* [n_leaves_u] */
+	double *wcov_d1;        /* [n_leaves_d] coverage w.r.t. refID1 */
+	double *wcov_d2;        /* [n_leaves_d] coverage w.r.t. refID2 */
+	double *genome_wcov_u;  /* [n_genomes+1], index 0 unused */
+	double *genome_wcov_d;  /* [n_genomes+1] */
+	uint64_t *genome_rcount_u; /* [n_genomes+1] */
+	uint64_t *genome_rcount_d; /* [n_genomes+1] */
+} cq_ilp_args;
+int cq_ilp_inputs(cq_ctx *ctx, const cq_index *idx, cq_ilp_args *io);
 
 /* ------------------------------------------- device-resident entry points (plumbing) -- */
 /*

@@ -20,6 +20,12 @@
  *       query64_* call like its "Time for query" bracket) and leaves with _exit so that the
  *       pointer-trie teardown (tens of seconds at 3e7 leaves) is not waited for
  *
+ *   ref_harness readdump <fastq> <min_len>
+ *       what FqReader::readFastq (query.cpp:371-425) holds after reading the file: one line
+ *       "<length> <bases>" per read on stdout ((uint8_t) length, the first `length` bytes as stored).
+ *       The reference seeds rand() from the clock; this binary interposes srand() so that
+ *       CAMMIQ_SEED (when set) is the seed instead, which makes the N substitution reproducible.
+ *
  * Canonical leaf ids in the dump = rank of the leaf's full key (h-base bucket prefix +
  * trie path) in lexicographic order within its table; both sides can compute it
  * independently of the bucket order in the file.
@@ -44,6 +50,13 @@
 #define private public
 #include "query.hpp"
 #undef private
+
+/* The reference calls srand(clock) at the top of readFastq; defined here, this srand wins over
+   libc's for every caller in the executable.  glibc's rand() shares its state with random(). */
+extern "C" void srand(unsigned int seed) {
+	const char *s = getenv("CAMMIQ_SEED");
+	srandom(s != NULL ? (unsigned int) atoi(s) : seed);
+}
 
 typedef std::unordered_map<const trieNode*, uint64_t> LeafIds;
 
@@ -125,7 +138,27 @@ static void runQuery(FqReader &fq, const std::string &mode, size_t fi) {
 		fq.query64_sc(fi);
 }
 
+static int readDump(const std::string &fastq, size_t min_len) {
+	std::string none;
+	FqReader fq(none, none, none, none, 0.01f, false);
+	fq.qfilenames.push_back(fastq);
+	fq.prepallFastq();
+	if (min_len == 0)
+		fq.readallFastq();
+	else
+		fq.readallFastq(min_len);
+	for (size_t r = 0; r < fq.reads[0].size(); r++) {
+		printf("%u ", (unsigned) fq.rlengths[0][r]);
+		fwrite(fq.reads[0][r], 1, fq.rlengths[0][r], stdout);
+		printf("\n");
+	}
+	fflush(stdout);
+	_exit(0);
+}
+
 int main(int argc, char **argv) {
+	if (argc == 4 && std::string(argv[1]) == "readdump")
+		return readDump(argv[2], (size_t) atol(argv[3]));
 	if (argc < 8) {
 		fprintf(stderr, "usage: see header of oracle/ref_harness.cpp\n");
 		return 2;

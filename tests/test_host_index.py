@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), "libcammiq_gpu.so does not export " + name
     assert declared == set(cq.capi.SYMBOLS), declared ^ set(cq.capi.SYMBOLS)
-    assert L.cq_abi_version() == 2
+    assert L.cq_abi_version() == cq.capi.ABI_VERSION == 3
 
 
 def test_no_device_fails_loudly():
