@@ -126,6 +126,8 @@ SYMBOLS = {
     "cq_reads_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "cq_reads_stage_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "cq_query_staged": (C.c_int, [C.c_void_p, C.c_int]),
+    "cq_query_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "cq_query_submit_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "cq_sync": (C.c_int, [C.c_void_p]),
     "cq_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "cq_get_device_counters": (C.c_int, [C.c_void_p, C.POINTER(DeviceCounters)]),
@@ -278,6 +280,8 @@ class Context:
 
     def _result(self, mode, n_reads, per_read, leaf_cap, want_rcount, pairs_cap, buffers=None):
         G, idx = self.n_genomes, self.index
+        if idx is None:
+            raise CammiqError(-7, "no index resident (call upload first)")
         res, keep = Result(), {}
         buffers = buffers or {}
         keep["cnt_u"] = buffers["cnt_u"] if "cnt_u" in buffers else np.zeros(G + 1, dtype=np.uint64)
@@ -381,6 +385,13 @@ class Context:
 
     def query_staged(self, mode):
         _check(lib().cq_query_staged(self._h, mode))
+
+    def submit(self, mode, bases, offsets, lengths, stride=0, packed=False):
+        """query() without the copy of the totals to the host (cq_query_submit[_packed]); the caller's
+        arrays must stay alive until sync()."""
+        fn = lib().cq_query_submit_packed if packed else lib().cq_query_submit
+        _check(fn(self._h, mode, bases.ctypes.data, offsets.ctypes.data if offsets is not None else None, stride,
+                  lengths.ctypes.data, len(lengths)))
 
     def sync(self):
         _check(lib().cq_sync(self._h))

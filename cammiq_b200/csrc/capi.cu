@@ -251,8 +251,10 @@ extern "C" void cq_ctx_destroy(cq_ctx *c) {
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 		if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
 		cudaFree(c->d_cbases[i]); cudaFree(c->d_coffsets[i]); cudaFree(c->d_coffsets32[i]); cudaFree(c->d_clengths[i]);
+		cudaFree(c->d_words[i]); cudaFree(c->d_len2[i]);
 		cudaFreeHost(c->h_pbases[i]); cudaFreeHost(c->h_plengths[i]); cudaFreeHost(c->h_poffsets[i]);
 	}
+	cudaFree(c->d_words[cq_ctx::kStages]); cudaFree(c->d_len2[cq_ctx::kStages]);
 	delete c->pool;
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	for (auto &se : c->steps)
@@ -361,6 +363,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	c->n_leaves_u = f.u.numLeaves();
 	c->n_leaves_d = f.d.numLeaves();
 	c->table_mask = f.n_table_buckets - 1;
+	c->table_shift = f.table_shift;
 	const size_t ncnt = 2 * ((size_t) n_genomes + 1);
 	CQ_CUDA(cudaMalloc((void **) &c->d_counts, (ncnt + 4) * sizeof(unsigned long long)));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u, std::max<size_t>(c->n_leaves_u, 1) * 4));
@@ -483,9 +486,9 @@ extern "C" int cq_reads_stage_packed(cq_ctx *c, const uint8_t *packed, const uin
 	return stageReads(c, true, packed, offsets, stride, lengths, n_reads);
 }
 
-// One launch of the scan (+ partial-count reduction) over a batch of reads resident on the
-// device.  `bases` is the address read offset 0 would have (the batch may hold only a slice
-// of the caller's base buffer), `first` is the caller's index of the batch's first read.
+// A batch of reads resident on the device as the caller holds them.  `bases` is the address read
+// offset 0 would have (the batch may hold only a slice of the caller's base buffer), `first` is
+// the caller's index of the batch's first read, `slot` the tile-layout buffer to use.
 struct ReadBatch {
 	const uint8_t *bases;
 	const uint64_t *offsets;
@@ -493,10 +496,48 @@ struct ReadBatch {
 	const uint8_t *lengths;
 	uint64_t n, first;
 	uint32_t max_len;
-	bool packed;               // 2-bit codes (ScanParams) instead of ASCII
+	bool packed;               // 2-bit bytes from the host packer instead of ASCII
 	const uint32_t *offsets32; // packed batches: batch-relative 32-bit offsets
+	int slot;                  // 0..kStages-1: pipeline stage, kStages: the staged reads
 };
 
+static uint32_t wordsPerRead(uint32_t longest) { return (((std::max<uint32_t>(longest, 1) + 15) / 16) + 2) | 1u; }
+
+// pack_tiles_kernel: the batch -> the scan's tile layout (+ validated lengths for ASCII input)
+static int launchPack(cq_ctx *c, const ReadBatch &rb) {
+	if (rb.n == 0)
+		return CQ_OK;
+	const int s = rb.slot;
+	PackParams q;
+	memset(&q, 0, sizeof(q));
+	q.words_per_read = wordsPerRead(rb.max_len);
+	q.n_reads = rb.n;
+	q.n_padded = (rb.n + 31) & ~31ull;
+	int rc;
+	if ((rc = ensure(&c->d_words[s], &c->cap_words[s], (size_t) q.n_padded * q.words_per_read)) != 0) return rc;
+	q.bases = rb.bases;
+	q.offsets = rb.offsets;
+	q.offsets32 = rb.offsets32;
+	q.stride = rb.stride;
+	q.read_base = rb.first;
+	q.lengths_in = rb.lengths;
+	q.words = c->d_words[s];
+	if (!rb.packed) {
+		if ((rc = ensure(&c->d_len2[s], &c->cap_len2[s], (size_t) rb.n)) != 0) return rc;
+		CQ_CUDA(cudaMemcpyAsync(c->d_len2[s], rb.lengths, rb.n, cudaMemcpyDeviceToDevice, c->stream));
+		q.lengths_out = c->d_len2[s];
+	}
+	const uint64_t threads = q.n_padded * q.words_per_read;
+	const unsigned blocks = (unsigned) ((threads + 255) / 256);
+	if (rb.packed)
+		pack_tiles_kernel<true><<<blocks, 256, 0, c->stream>>>(q);
+	else
+		pack_tiles_kernel<false><<<blocks, 256, 0, c->stream>>>(q);
+	c->timing.kernel_launches++;
+	return CQ_OK;
+}
+
+// One launch of the scan (+ partial-count reduction) over a batch launchPack has prepared.
 static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	if (rb.n == 0)
 		return CQ_OK;
@@ -505,6 +546,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	memset(&sp, 0, sizeof(sp));
 	sp.table = c->d_table;
 	sp.table_mask = c->table_mask;
+	sp.table_shift = c->table_shift;
 	sp.nodes_u = c->d_nodes_u;
 	sp.nodes_d = c->d_nodes_d;
 	sp.leaf_u_ref = c->d_leaf_u_ref;
@@ -513,23 +555,14 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.n_genomes = c->n_genomes;
 	sp.filter = c->d_filter;
 	sp.filter_words = c->filter_words;
-	sp.bases = rb.bases;
-	sp.offsets = rb.offsets;
-	sp.offsets32 = rb.offsets32;
-	sp.stride = rb.stride;
-	sp.read_base = rb.first;
-	sp.lengths = rb.lengths;
+	sp.words = c->d_words[rb.slot];
+	sp.lengths = rb.packed ? rb.lengths : c->d_len2[rb.slot];
 	sp.n_reads = rb.n;
-	// raw staging buffer: the byte range 32 back-to-back reads of the longest length span
-	// (+ alignment slack); sparser layouts fall back to direct global loads inside the kernel.
-	// packed buffer: 16 bases per word, two words of slack per read (three-word windows), odd
-	// stride so that the lanes' reads start in different banks
+	// two tile buffers per warp: 16 bases per word, two words of slack per read (three-word
+	// windows), odd stride so that the lanes' reads start in different banks
 	const uint32_t longest = std::max<uint32_t>(rb.max_len, 1);
-	const uint32_t read_bytes = rb.packed ? (longest + 3) / 4 : longest;
-	const uint32_t tile_cap = (32 * read_bytes + (rb.packed ? 64 : 32) + 127) & ~127u;
-	sp.tile_cap = tile_cap;
-	sp.words_per_read = (((longest + 15) / 16) + 2) | 1u;
-	const size_t dyn_smem = (size_t) kWarpsPerBlock * (tile_cap + kTileSlack + 32 * sp.words_per_read * 4) + c->smem_bytes;
+	sp.words_per_read = wordsPerRead(longest);
+	const size_t dyn_smem = (size_t) kWarpsPerBlock * kTileBufs * 32 * sp.words_per_read * 4 + c->smem_bytes;
 	// a read can reach 2 tables x 2 strands x (longest - h + 1) leaves; what exceeds the shared
 	// hit slots spills to global scratch, sized (and grown) for the longest read seen so far
 	const uint32_t max_hits = longest >= c->h ? 4 * (longest - c->h + 1) : 0;
@@ -570,12 +603,10 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 		sp.read_leaf_d = c->d_leaf_d + rb.first * c->leaf_cap;
 	}
 	const bool filt = c->d_filter != NULL;
-	static const void *const kernels[8] = {
-		(const void *) scan_reads_kernel<CQ_MODE_P, false, false>, (const void *) scan_reads_kernel<CQ_MODE_P, false, true>,
-		(const void *) scan_reads_kernel<CQ_MODE_P, true, false>, (const void *) scan_reads_kernel<CQ_MODE_P, true, true>,
-		(const void *) scan_reads_kernel<CQ_MODE_SC, false, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, false, true>,
-		(const void *) scan_reads_kernel<CQ_MODE_SC, true, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, true, true>};
-	const int variant = mode * 4 + (filt ? 2 : 0) + (rb.packed ? 1 : 0);
+	static const void *const kernels[4] = {
+		(const void *) scan_reads_kernel<CQ_MODE_P, false>, (const void *) scan_reads_kernel<CQ_MODE_P, true>,
+		(const void *) scan_reads_kernel<CQ_MODE_SC, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, true>};
+	const int variant = mode * 2 + (filt ? 1 : 0);
 	const void *kern = kernels[variant];
 	if (dyn_smem != c->last_dyn_smem[variant]) {
 		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
@@ -588,8 +619,22 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 		if (getenv("CAMMIQ_MAX_BLOCKS"))
 			c->last_per_sm[variant] = std::min(c->last_per_sm[variant], atoi(getenv("CAMMIQ_MAX_BLOCKS")));
 		cudaFuncAttributes fa;
-		if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess)
+		size_t static_smem = 0;
+		if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
 			c->timing.regs_per_thread = (uint32_t) fa.numRegs;
+			static_smem = fa.sharedSizeBytes;
+		}
+		// The probes in flight live in the SM's L1 (a random gather holds a 128-byte line while it is
+		// outstanding; tools/microbench_l1.py: 284 G gathers/s with the whole 256 KB as L1, 82 G/s with
+		// 28 KB), and L1 is what the shared-memory carve-out leaves.  Left to itself the driver sizes
+		// the carve-out for the occupancy the kernel COULD reach; ask for what this launch uses.
+		const size_t per_block = dyn_smem + static_smem + 1024;
+		int pct = (int) ((per_block * (size_t) c->last_per_sm[variant] * 100 + 228 * 1024 - 1) / (228 * 1024));
+		pct = std::max(1, std::min(100, pct));
+		if (getenv("CAMMIQ_CARVEOUT"))
+			pct = atoi(getenv("CAMMIQ_CARVEOUT"));
+		if (pct >= 0)
+			CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
 	}
 	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads; // one 32-read sub-tile per warp at least
 	c->grid = (int) std::min<uint64_t>((uint64_t) c->last_per_sm[variant] * c->n_sms, n_tiles);
@@ -673,9 +718,10 @@ extern "C" int cq_query_staged(cq_ctx *c, int mode) {
 	cudaEvent_t *sev;
 	if ((rc = beginStep(c, &sev)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[0], c->stream));
-	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	ReadBatch rb = {c->d_bases - c->staged_shift, c->staged_has_offsets ? c->d_offsets : NULL, c->staged_stride, c->d_lengths,
-		c->staged_reads, 0, c->staged_max_len, c->staged_packed, NULL};
+		c->staged_reads, 0, c->staged_max_len, c->staged_packed, NULL, cq_ctx::kStages};
+	if ((rc = launchPack(c, rb)) != 0) return rc;
+	CQ_CUDA(cudaEventRecord(sev[1], c->stream));
 	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 	CQ_CUDA(cudaEventRecord(sev[2], c->stream));
 	CQ_CUDA(cudaEventRecord(sev[3], c->stream));
@@ -854,7 +900,8 @@ static int pipelineDirect(cq_ctx *c, int mode, bool packed, const uint8_t *bases
 		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
 		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
 		ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len,
-			packed, NULL};
+			packed, NULL, b};
+		if ((rc = launchPack(c, rb)) != 0) return rc;
 		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
 	}
@@ -903,7 +950,8 @@ static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uin
 		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
 		// fixed stride: the kernel addresses read r at (first + r) * stride
 		ReadBatch rb = {dense ? c->d_cbases[b] : c->d_cbases[b] - first * layout.stride, NULL, layout.stride, c->d_clengths[b], n,
-			first, std::max<uint32_t>(layout.max_len, 1), true, dense ? c->d_coffsets32[b] : NULL};
+			first, std::max<uint32_t>(layout.max_len, 1), true, dense ? c->d_coffsets32[b] : NULL, b};
+		if ((rc = launchPack(c, rb)) != 0) return rc;
 		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
 		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
 	}
@@ -976,6 +1024,16 @@ extern "C" int cq_query(cq_ctx *c, int mode, const uint8_t *bases, const uint64_
 extern "C" int cq_query_packed(cq_ctx *c, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads, cq_result *out) {
 	return queryHost(c, mode, true, packed, offsets, stride, lengths, n_reads, out, "cq_query_packed");
+}
+
+extern "C" int cq_query_submit(cq_ctx *c, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	return cqSubmitHost(c, mode, false, bases, offsets, stride, lengths, n_reads, NULL, "cq_query_submit");
+}
+
+extern "C" int cq_query_submit_packed(cq_ctx *c, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads) {
+	return cqSubmitHost(c, mode, true, packed, offsets, stride, lengths, n_reads, NULL, "cq_query_submit_packed");
 }
 
 extern "C" int cq_ctx_set_host_packing(cq_ctx *c, int threads) {

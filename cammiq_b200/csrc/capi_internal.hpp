@@ -47,6 +47,7 @@ struct cq_ctx {
 	bool has_index = false;
 	uint32_t h = 0, n_genomes = 0;
 	uint64_t n_leaves_u = 0, n_leaves_d = 0, table_mask = 0;
+	uint32_t table_shift = 26;
 	TableBucket *d_table = NULL;
 	uint32_t *d_nodes_u = NULL, *d_nodes_d = NULL, *d_leaf_u_ref = NULL;
 	uint2 *d_leaf_d_ref = NULL;
@@ -74,9 +75,8 @@ struct cq_ctx {
 	uint32_t staged_max_len = 0;
 	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
 	bool staged_packed = false;
-	size_t last_dyn_smem[8] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1,
-		(size_t) -1}; // per kernel variant
-	int last_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	size_t last_dyn_smem[4] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
+	int last_per_sm[4] = {0, 0, 0, 0};
 	// host->device pipeline of cq_query: kStages chunk buffers rotate through copy and scan
 	static const int kStages = 3;
 	cudaStream_t copy_stream = NULL;
@@ -87,6 +87,11 @@ struct cq_ctx {
 	uint8_t *d_clengths[kStages] = {NULL, NULL, NULL};
 	size_t cap_cbases[kStages] = {0, 0, 0}, cap_coffsets[kStages] = {0, 0, 0}, cap_coffsets32[kStages] = {0, 0, 0},
 		cap_clengths[kStages] = {0, 0, 0};
+	// reads in the scan's tile layout (pack_tiles_kernel): one buffer per pipeline stage + one
+	// for the staged reads (index kStages); the length copies hold 0 for reads found invalid
+	uint32_t *d_words[kStages + 1] = {NULL, NULL, NULL, NULL};
+	uint8_t *d_len2[kStages + 1] = {NULL, NULL, NULL, NULL};
+	size_t cap_words[kStages + 1] = {0, 0, 0, 0}, cap_len2[kStages + 1] = {0, 0, 0, 0};
 	// host packing (cq_ctx_set_host_packing): worker pool + pinned staging of the packed chunks
 	int pack_threads = 0;
 	WorkerPool *pool = NULL;

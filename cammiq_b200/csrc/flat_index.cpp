@@ -51,8 +51,8 @@ inline int bucketInsert(TableBucket &b, uint64_t key, bool &fresh) {
 
 // Insert (or find) key; returns the slot.  Linear probing by bucket; every full bucket passed
 // on the way gets its overflow flag, so lookups know to look further.
-inline SlotRef probeInsert(RawArray<TableBucket> &t, uint64_t mask, uint32_t h, uint64_t key, bool &fresh) {
-	uint64_t b = homeBucketHost(key, h, mask);
+inline SlotRef probeInsert(RawArray<TableBucket> &t, uint64_t mask, uint32_t shift, uint32_t h, uint64_t key, bool &fresh) {
+	uint64_t b = homeBucketHost(key, h, shift);
 	for (;;) {
 		const int k = bucketInsert(t[b], key, fresh);
 		if (k >= 0) {
@@ -82,9 +82,17 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 	uint64_t upper = u.bucket_key.size() + d.bucket_key.size();
 	uint64_t want = (uint64_t) ((double) upper / (load_factor * kSlotsPerBucket)) + 1;
 	uint64_t nb = 64;
-	while (nb < want)
+	uint32_t shift = 26;
+	while (nb < want && shift > 0) {
 		nb <<= 1;
+		shift--;
+	}
+	if (nb < want) {
+		err = "Index too large: the prefix table would need more than 2^32 buckets.";
+		return CQ_ENOMEM;
+	}
 	out.n_table_buckets = nb;
+	out.table_shift = shift;
 	// the table is a few GB: allocate it raw and first-touch it from all threads
 	if (!out.table.alloc(nb))
 		throw std::bad_alloc();
@@ -120,7 +128,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 			pool.emplace_back([&, q, t]() {
 				const size_t a = x.bucket_key.size() * q / T, e = x.bucket_key.size() * (q + 1) / T;
 				for (size_t i = a; i < e; i++) {
-					const uint64_t b = homeBucketHost(x.bucket_key[i], u.hash_len, mask);
+					const uint64_t b = homeBucketHost(x.bucket_key[i], u.hash_len, shift);
 					unsigned p = (unsigned) (((unsigned __int128) b * T) / nb);
 					while (p + 1 < T && b >= nb * (p + 1) / T) p++;
 					while (p > 0 && b < nb * p / T) p--;
@@ -179,7 +187,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 					for (size_t i = 0; i < x.bucket_key.size(); i++) {
 						if (own[i] != (uint8_t) p)
 							continue;
-						Pending e = {(uint64_t) i, homeBucketHost(x.bucket_key[i], u.hash_len, mask)};
+						Pending e = {(uint64_t) i, homeBucketHost(x.bucket_key[i], u.hash_len, shift)};
 						__builtin_prefetch(&out.table[e.b * kSlotsPerBucket], 1);
 						if (queued >= kAhead)
 							insert(ring[queued % kAhead]); // the oldest entry: file order is kept
@@ -206,7 +214,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 			bool fresh;
 			// the flags of the owner's range are already raised; from the range end on, the key
 			// wraps into buckets of another (finished) range
-			SlotRef s = probeInsert(out.table, mask, u.hash_len, x.bucket_key[df.index], fresh);
+			SlotRef s = probeInsert(out.table, mask, shift, u.hash_len, x.bucket_key[df.index], fresh);
 			n_keys += fresh ? 1 : 0;
 			s.b->ref[s.k][df.table] = x.bucket_root[df.index];
 		}
@@ -266,7 +274,7 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
 			return UINT64_MAX;
 	}
-	uint64_t b = homeBucketHost(bucket, fi.hash_len, mask);
+	uint64_t b = homeBucketHost(bucket, fi.hash_len, fi.table_shift);
 	uint32_t ref = kRefNone;
 	const uint64_t tag = bucket | kKeyOccupied;
 	for (;;) {

@@ -77,10 +77,6 @@ inline uint64_t canonicalKeyHost(uint64_t key, uint32_t h) {
 	return key < rc ? key : rc;
 }
 
-// Home bucket of a key.  Keys are stored as they are, but PLACED by their canonical h-mer: a key
-// and its reverse complement share one probe sequence, so the scan -- which holds both strands'
-// hashes of a window -- finds either with ONE bucket load per read position.
-inline uint64_t homeBucketHost(uint64_t key, uint32_t h, uint64_t mask) { return mixKey(canonicalKeyHost(key, h)) & mask; }
 
 #if defined(__CUDACC__)
 __host__ __device__
@@ -89,6 +85,22 @@ inline void filterHash(uint64_t key, uint32_t &A, uint32_t &B) {
 	const uint32_t lo = (uint32_t) key, hi = (uint32_t) (key >> 32);
 	A = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
 	B = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
+}
+// Home bucket of a key.  Keys are stored as they are, but PLACED by their canonical h-mer: a key
+// and its reverse complement share one probe sequence, so the scan -- which holds both strands'
+// hashes of a window -- finds either with ONE bucket load per read position.  The bucket is a
+// multiplicative hash of the filter hash B the scan has computed for the position anyway: the
+// moment a position passes the filter its bucket address costs two more instructions, cheap
+// enough to request the sector from HBM right there (prefetch), long before phase 2 needs it.
+// table_shift = 32 - log2(number of buckets); the table has between 2^6 and 2^32 buckets.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint64_t tableBucket(uint32_t B, uint32_t table_shift) { return (uint64_t) ((B * 0x9E3779B1u) >> table_shift); }
+inline uint64_t homeBucketHost(uint64_t key, uint32_t h, uint32_t table_shift) {
+	uint32_t A, B;
+	filterHash(canonicalKeyHost(key, h), A, B);
+	return tableBucket(B, table_shift);
 }
 // word index for a filter of `words` words (any count below 2^32): the high half of A * words
 #if defined(__CUDACC__)
@@ -167,7 +179,8 @@ struct RawArray {
 
 struct FlatIndex {
 	uint32_t hash_len = 0;
-	uint64_t n_table_buckets = 0; // power of two
+	uint64_t n_table_buckets = 0; // power of two, 2^6 .. 2^32
+	uint32_t table_shift = 26;    // 32 - log2(n_table_buckets)
 	uint64_t n_keys = 0;
 	RawArray<TableBucket> table;  // n_table_buckets
 	std::vector<uint64_t> filter; // any multiple of 128 words, empty = no filter (index too large for L2)

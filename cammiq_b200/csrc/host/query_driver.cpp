@@ -13,16 +13,7 @@
 #include <sstream>
 #include <thread>
 
-#ifdef CAMMIQ_WITH_NCCL
-#include <cuda_runtime.h>
-#include <nccl.h>
-#endif
-
 namespace cammiq {
-
-#ifdef CAMMIQ_WITH_NCCL
-static std::vector<ncclComm_t> g_comms; // one communicator per GPU of this process
-#endif
 
 static uint64_t nowMs() {
 	return (uint64_t) std::chrono::duration_cast<std::chrono::milliseconds>(
@@ -53,8 +44,7 @@ FqReader::FqReader(uint32_t hl_u, const std::string &idx_u, uint32_t hl_d, const
 FqReader::~FqReader() {
 	if (ctx_thread.joinable())
 		ctx_thread.join();
-	for (auto c : ctxs)
-		cq_ctx_destroy(c);
+	cq_multi_destroy(multi);
 	if (index != NULL)
 		cq_index_free(index);
 	for (auto g : genomes)
@@ -66,12 +56,11 @@ FqReader::~FqReader() {
 // FqReader::loadIdx_p (query.cpp:109-123): both index files are decoded on two host threads
 // inside cq_index_load and flattened into the device layout.
 void FqReader::startContexts() {
-	ctxs.assign((size_t) n_gpus, NULL);
-	ctx_rc.assign((size_t) n_gpus, 0);
+	ctx_rc = 0;
 	ctx_thread = std::thread([this]() {
-		for (int d = 0; d < n_gpus; d++)
-			if ((ctx_rc[(size_t) d] = cq_ctx_create(d, NULL, &ctxs[(size_t) d])) != 0 && ctx_err.empty())
-				ctx_err = cq_last_error();
+		// one context per GPU (and their NCCL communicator when there are several)
+		if ((ctx_rc = cq_multi_create(n_gpus, NULL, &multi)) != 0)
+			ctx_err = cq_last_error(); // the error text is per thread: kept for the report
 	});
 }
 
@@ -138,29 +127,15 @@ void FqReader::loadSmap() {
 	else
 		startContexts(), ctx_thread.join();
 	const uint64_t t_up = nowMs();
-	for (int d = 0; d < n_gpus; d++) {
-		if (ctx_rc[(size_t) d] != 0 || ctxs[(size_t) d] == NULL) {
-			fprintf(stderr, "Cannot create the GPU context: %s\n", ctx_err.c_str());
-			abort();
-		}
-		if (cq_index_upload(ctxs[(size_t) d], index, G) != 0)
-			die("Cannot place the index on the GPU");
+	if (ctx_rc != 0 || multi == NULL) {
+		fprintf(stderr, "Cannot create the GPU context: %s\n", ctx_err.c_str());
+		abort();
 	}
+	if (cq_multi_upload(multi, index, G) != 0)
+		die("Cannot place the index on the GPU");
 	if (getenv("CAMMIQ_VERBOSE"))
 		fprintf(stderr, "[cammiq] waited %lu ms for the GPU context(s), index upload %lu ms\n",
 			(unsigned long) (t_up - t_ctx), (unsigned long) (nowMs() - t_up));
-#ifdef CAMMIQ_WITH_NCCL
-	if (n_gpus > 1 && g_comms.empty()) {
-		// communicator set-up belongs to start-up (like the index load), not to "Time for query"
-		g_comms.resize(n_gpus);
-		std::vector<int> devs(n_gpus);
-		for (int d = 0; d < n_gpus; d++) devs[d] = d;
-		if (ncclCommInitAll(g_comms.data(), n_gpus, devs.data()) != ncclSuccess) {
-			fprintf(stderr, "ncclCommInitAll failed.\n");
-			abort();
-		}
-	}
-#endif
 }
 
 // FqReader::loadGenomeLength (query.cpp:158-205)
@@ -261,75 +236,10 @@ void FqReader::queryGpu(size_t file_idx, int mode) {
 		res.pairs = pairs.data();
 		res.pairs_cap = pairs.size();
 	}
-	const int ng = (int) ctxs.size();
-	if (ng == 1) {
-		if (cq_query_packed(ctxs[0], mode, rs.bases, rs.offsets.data(), 0, rs.lengths.data(), n, &res) != 0)
-			die("GPU query failed");
-	} else {
-		// reads sharded over the GPUs (index replicated), counters combined afterwards
-		std::vector<int> rcs(ng, 0);
-		std::vector<std::thread> pool;
-		for (int d = 0; d < ng; d++)
-			pool.emplace_back([&, d]() {
-				uint64_t lo = n * d / ng, hi = n * (d + 1) / ng;
-				rcs[d] = cq_reads_stage_packed(ctxs[d], rs.bases, rs.offsets.data() + lo, 0, rs.lengths.data() + lo, hi - lo);
-				if (rcs[d] == 0) rcs[d] = cq_query_staged(ctxs[d], mode);
-				if (rcs[d] == 0) rcs[d] = cq_sync(ctxs[d]);
-			});
-		for (auto &t : pool) t.join();
-		for (int d = 0; d < ng; d++)
-			if (rcs[d] != 0) die("GPU query failed");
-#ifdef CAMMIQ_WITH_NCCL
-		if (mode == CQ_MODE_P) {
-			// one NCCL sum-reduce of the counter block (+ per-leaf rcount) into GPU 0
-			std::vector<ncclComm_t> &comms = g_comms;
-			ncclGroupStart();
-			for (int d = 0; d < ng; d++) {
-				cq_device_counters dc;
-				void *st = NULL;
-				cq_get_device_counters(ctxs[d], &dc);
-				cq_get_stream(ctxs[d], &st);
-				cudaSetDevice(d);
-				ncclReduce(dc.d_counts, dc.d_counts, dc.n_counts, ncclUint64, ncclSum, 0, comms[d], (cudaStream_t) st);
-				if (dc.n_rcount_u) ncclReduce(dc.d_rcount_u, dc.d_rcount_u, dc.n_rcount_u, ncclUint32, ncclSum, 0, comms[d], (cudaStream_t) st);
-				if (dc.n_rcount_d) ncclReduce(dc.d_rcount_d, dc.d_rcount_d, dc.n_rcount_d, ncclUint32, ncclSum, 0, comms[d], (cudaStream_t) st);
-			}
-			ncclGroupEnd();
-			for (int d = 0; d < ng; d++) cq_sync(ctxs[d]);
-			if (cq_fetch(ctxs[0], mode, &res) != 0) die("GPU fetch failed");
-			// ranks > 0 hold only their own share; drop it so the next file starts clean
-			for (int d = 1; d < ng; d++) cq_reset(ctxs[d]);
-		} else
-#endif
-		{
-			// host-side combine (pair maps are merged on the host in any case)
-			std::map<std::pair<uint32_t, uint32_t>, uint64_t> pm;
-			std::vector<uint64_t> tu(G + 1, 0), td(G + 1, 0);
-			std::vector<uint32_t> ru(rcount_u.size(), 0), rd(rcount_d.size(), 0);
-			uint64_t und = 0, conf = 0, inv = 0;
-			for (int d = 0; d < ng; d++) {
-				if (cq_fetch(ctxs[d], mode, &res) != 0) die("GPU fetch failed");
-				for (uint32_t g = 0; g <= G; g++) { tu[g] += cu[g]; td[g] += cd[g]; }
-				if (mode == CQ_MODE_P) {
-					for (size_t i = 0; i < ru.size(); i++) ru[i] += rcount_u[i];
-					for (size_t i = 0; i < rd.size(); i++) rd[i] += rcount_d[i];
-				}
-				for (uint64_t i = 0; i < res.n_pairs; i++)
-					pm[std::make_pair(pairs[i].a, pairs[i].b)] += pairs[i].count;
-				und += res.nundet; conf += res.nconf; inv += res.n_invalid;
-			}
-			cu = tu; cd = td;
-			if (mode == CQ_MODE_P) { rcount_u = ru; rcount_d = rd; }
-			res.nundet = und; res.nconf = conf; res.n_invalid = inv;
-			res.n_pairs = 0;
-			for (auto &it : pm) {
-				pairs[res.n_pairs].a = it.first.first;
-				pairs[res.n_pairs].b = it.first.second;
-				pairs[res.n_pairs].count = it.second;
-				res.n_pairs++;
-			}
-		}
-	}
+	// reads sharded over the GPUs (index replicated), counters combined by one NCCL reduce: all
+	// of it behind the ABI; with one GPU this is cq_query_packed
+	if (cq_multi_query_packed(multi, mode, rs.bases, rs.offsets.data(), 0, rs.lengths.data(), n, &res) != 0)
+		die("GPU query failed");
 	for (uint32_t g = 1; g <= G; g++) {
 		genomes[g]->read_cnts_u = cu[g];
 		genomes[g]->read_cnts_d = cd[g];
@@ -342,7 +252,9 @@ void FqReader::queryGpu(size_t file_idx, int mode) {
 		for (uint64_t i = 0; i < res.n_pairs; i++)
 			read_cnts_b[std::make_pair(pairs[i].a, pairs[i].b)] = pairs[i].count;
 	}
-	fprintf(stderr, "Processed %lu reads.\r", (unsigned long) n);
+	// the reference's progress line appears before every 100 000th read (query.cpp:637-638)
+	for (uint64_t nrd = 0; nrd < n; nrd += 100000)
+		fprintf(stderr, "Processed %lu reads.\r", (unsigned long) (nrd + 1));
 	fprintf(stderr, "\nNumber of unlabeled reads: %lu.\n", (unsigned long) nundet);
 	fprintf(stderr, "Number of reads with conflict labels: %lu.\n", (unsigned long) nconf);
 	if (ninvalid > 0)
@@ -364,8 +276,7 @@ void FqReader::resetCounters(bool sc) {
 		std::fill(rcount_u.begin(), rcount_u.end(), 0);
 		std::fill(rcount_d.begin(), rcount_d.end(), 0);
 	}
-	for (auto c : ctxs)
-		if (cq_reset(c) != 0) die("cq_reset failed");
+	if (cq_multi_reset(multi) != 0) die("cq_reset failed");
 	fprintf(stderr, "Time for resetting counters: %lu ms.\n", (unsigned long) (nowMs() - start));
 }
 

@@ -64,10 +64,10 @@ private:
 	bool debug_display;
 
 	cq_index *index = NULL;
-	std::vector<cq_ctx *> ctxs;
+	cq_multi *multi = NULL; // the GPU(s): cq_multi_* shards reads and reduces the counters
 	// the GPU contexts come up on a thread of their own while the host decodes the index
 	std::thread ctx_thread;
-	std::vector<int> ctx_rc;
+	int ctx_rc = 0;
 	std::string ctx_err; // cq_last_error() is per thread: kept for the report
 	void startContexts();
 	std::vector<uint32_t> rcount_u, rcount_d; // pleafNode::rcount in file order

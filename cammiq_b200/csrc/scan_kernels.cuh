@@ -1,12 +1,17 @@
 // sm_100a kernels of the read-matching path.
 //
-//   scan_reads_kernel      A1-A8 in one launch, persistent grid.  Every WARP owns tiles of 32
+//   pack_tiles_kernel      reads as the caller holds them (ASCII, or 2-bit bytes packed by the host)
+//                          -> the scan's tile layout: 16 bases per 32-bit word, first base in the
+//                          top bits, a fixed number of words per read.  ASCII is decoded and
+//                          validated here (A1).  Streaming, coalesced, HBM-bound.
+//   scan_reads_kernel      A2-A8 in one launch, persistent grid.  Every WARP owns tiles of 32
 //                          reads and runs four steps per tile, with no block-wide barrier:
-//                            stage    one TMA bulk copy (cp.async.bulk + the warp's mbarrier)
-//                                     brings the tile's bytes into shared memory; lane r turns
-//                                     read r into 2-bit codes, 16 bases per 32-bit word (ASCII
-//                                     input is decoded and validated here), after which the raw
-//                                     buffer is free and the NEXT tile's copy is issued at once;
+//                            stage    one TMA bulk copy (cp.async.bulk + mbarrier) brings the
+//                                     tile's words into one of the warp's two shared-memory
+//                                     buffers; the NEXT tile's copy is issued before this tile is
+//                                     scanned.  The kernel keeps its shared memory small on
+//                                     purpose: the in-flight probes live in the SM's L1, which is
+//                                     what is left of the 256 KB after the carve-out;
 //                            phase 1  the tile's read positions are cut into strips of 8; a lane
 //                                     takes a strip, extracts its first h-mer from three packed
 //                                     words, rolls the hashes of BOTH strands through the strip
@@ -52,18 +57,22 @@ static const int kWarpsPerBlock = kScanThreads / 32;
 #endif
 static const int kStrip = CAMMIQ_STRIP;       // read positions per lane and phase-1 round (that many probes in flight per lane)
 static const int kQueueCap = 512;             // per-warp candidate queue; a round adds at most 32 * kStrip
-static const int kHitSeg = 8;                 // per-read hit slots in shared memory (the rest spills to global)
+static const int kHitSeg = 4;                 // per-read hit slots in shared memory (the rest spills to global)
+#ifndef CAMMIQ_TILE_BUFS
+#define CAMMIQ_TILE_BUFS 1
+#endif
+static const int kTileBufs = CAMMIQ_TILE_BUFS; // 2: the next tile's copy overlaps the scan of this one
 static const int kLightHits = 16;             // longer hit lists are deduplicated by the whole warp
 static const int kProbeUnroll = 4;            // micro-benchmark unroll
 static const int kMaxBlocksPerSM = 4;
 static const uint32_t kMaxSmemGenomes = 8191; // 2*(G+1) u32 block counters must fit 64 KB
-static const uint32_t kTileSlack = 32;        // bytes readable past a staged tile (unaligned 20-byte windows)
 static const uint32_t kSetEmpty = 0xFFFFFFFFu;
 
 struct ScanParams {
 	// index
 	const TableBucket *table;
 	uint64_t table_mask;
+	uint32_t table_shift;     // home bucket of a key = tableBucket(filter hash B of its canonical h-mer, table_shift)
 	const uint2 *filter;      // NULL: no filter, phase 1 probes the table
 	uint32_t filter_words;    // number of 64-bit filter words
 	const uint32_t *nodes_u, *nodes_d;
@@ -71,19 +80,13 @@ struct ScanParams {
 	const uint2 *leaf_d_ref;
 	uint32_t h;
 	uint32_t n_genomes;
-	// reads in device memory.  ASCII (exactly the state query64_* consumes), or PACKED: 2 bits per
-	// base, base j of a read in byte j/4 at bits 7-2*(j%4)..6-2*(j%4) (first base most
-	// significant), ceil(len/4) bytes per read, validated on the host (an invalid read arrives
-	// with length 0)
-	const uint8_t *bases;
-	const uint64_t *offsets;  // NULL: read i starts at (read_base + i)*stride
-	const uint32_t *offsets32; // PACKED only: 32-bit offsets (batch-relative), or NULL
-	uint64_t stride;
-	uint64_t read_base;       // caller's index of this launch's first read (chunked submission)
+	// reads in the tile layout pack_tiles_kernel writes: read r = words[r * words_per_read ..),
+	// 16 bases per word, first base in the top bits, zero past the read's end; whole tiles of 32
+	// reads are present (the padding reads are zero).  lengths[r] = 0 marks an invalid read.
+	const uint32_t *words;
 	const uint8_t *lengths;
 	uint64_t n_reads;
-	uint32_t tile_cap;        // bytes of a warp's raw staging buffer (32 reads as they arrive)
-	uint32_t words_per_read;  // 32-bit words per read in the warp's packed buffer: ceil(longest/16) + 2, odd
+	uint32_t words_per_read;  // ceil(longest/16) + 2, odd (the lanes' reads start in different banks)
 	// outputs
 	int smem_counters;        // 1: block-private genome counters + partials, 0: global atomics
 	uint32_t *partials;       // [gridDim.x][2*(G+1)]
@@ -152,6 +155,10 @@ __device__ __forceinline__ void redAddStream(uint32_t *a, unsigned long long pol
 	asm volatile("red.global.add.L2::cache_hint.u32 [%0], 1, %1;" ::"l"(a), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ void prefetchL2(const void *a) {
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
+
 __device__ __forceinline__ uint32_t smemAddr(const void *p) {
 	return (uint32_t) __cvta_generic_to_shared(p);
 }
@@ -199,7 +206,7 @@ struct WarpState {
 	uint16_t strip_base[34];       // exclusive prefix sum of the reads' strip counts, [32] = total
 	uint8_t rl[32];
 	uint32_t set_cnt[2];           // cooperative dedup: distinct U / D leaves of the read in work
-	uint64_t bar;                  // mbarrier of the warp's raw staging buffer
+	uint64_t bar[2];               // mbarriers of the warp's two tile buffers
 };
 
 // base j of a packed read (16 bases per word, first base in the top bits)
@@ -239,7 +246,7 @@ __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__rest
 }
 
 // Leaves under a bucket root reached by one strand of a read go to the read's hit list.
-template <bool REVERSE>
+template <bool REVERSE, int MODE>
 __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws, uint32_t *warp_spill, uint32_t pk_addr,
 		uint32_t slot, uint32_t rl, uint32_t next, unsigned long long refs, uint32_t &n_leaf_hits) {
 	uint32_t leaf[2];
@@ -250,6 +257,13 @@ __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws
 		if (leaf[t] == kRefNone)
 			continue;
 		n_leaf_hits++;
+		// what phase 3 will touch for this leaf -- its genome ids and (mode P) its read counter --
+		// is requested now, so that phase 3 finds it in L2
+		const uint32_t lid = leaf[t] & ~kRefLeafTag;
+		if (t) prefetchL2(&p.leaf_d_ref[lid]);
+		else prefetchL2(&p.leaf_u_ref[lid]);
+		if (MODE == CQ_MODE_P)
+			prefetchL2(t ? &p.rcount_d[lid] : &p.rcount_u[lid]);
 		uint32_t e = (leaf[t] & ~kRefLeafTag) | (t ? kRefLeafTag : 0u);
 		// 16-bit shared counter bumped through its containing 32-bit word
 		uint32_t *word = reinterpret_cast<uint32_t *>(&ws.hit_cnt[slot & ~1u]);
@@ -265,6 +279,7 @@ __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws
 // strands of a window share the probe sequence and ONE bucket load serves both), descend, append
 // leaves to the read's hit list.  A palindromic h-mer (its own reverse complement) is found by
 // both strands: the two tags are equal and both descents run.
+template <int MODE>
 __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, uint32_t pk_warp, uint32_t *warp_spill,
 		int lane, uint32_t nq, uint32_t &n_leaf_hits, uint32_t &n_chained) {
 	__syncwarp();
@@ -279,7 +294,9 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 			const uint32_t rl = ws.rl[slot];
 			const unsigned long long hf = packedWindow(pk_addr, i, h), hr = revcompKey(hf, h);
 			const unsigned long long tag_f = hf | kKeyOccupied, tag_r = hr | kKeyOccupied;
-			uint64_t b = mixKey(hf < hr ? hf : hr) & p.table_mask;
+			uint32_t A, B;
+			filterHash(hf < hr ? hf : hr, A, B);
+			uint64_t b = tableBucket(B, p.table_shift); // requested from HBM when phase 1 found the candidate
 			unsigned long long refs_f = 0, refs_r = 0;
 			bool found_f = !(strands & 1u), found_r = !(strands & 2u); // "nothing left to find" per strand
 			bool hit_f = false, hit_r = false;
@@ -301,24 +318,24 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 				n_chained++;
 			}
 			if (hit_f)
-				collectLeaves<false>(p, ws, warp_spill, pk_addr, slot, rl, i + h, refs_f, n_leaf_hits);
+				collectLeaves<false, MODE>(p, ws, warp_spill, pk_addr, slot, rl, i + h, refs_f, n_leaf_hits);
 			if (hit_r)
-				collectLeaves<true>(p, ws, warp_spill, pk_addr, slot, rl, i, refs_r, n_leaf_hits);
+				collectLeaves<true, MODE>(p, ws, warp_spill, pk_addr, slot, rl, i, refs_r, n_leaf_hits);
 		}
 	}
 	__syncwarp();
 }
 
-template <int MODE, bool FILTER, bool PACKED>
+template <int MODE, bool FILTER>
 __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_kernel(ScanParams p) {
-	// [8 warps][tile_cap + slack: raw tile] | [8 warps][32 * words_per_read: packed tile] | [2*(G+1) u32 genome counters]
+	// [8 warps][kTileBufs buffers][32 * words_per_read words: a packed tile] | [2*(G+1) u32 genome counters]
 	extern __shared__ __align__(128) uint8_t dyn_smem[];
 	__shared__ __align__(16) WarpState warp_state[kWarpsPerBlock];
 	__shared__ unsigned long long block_tot[2]; // nundet, nconf
 
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-	const uint32_t raw_bytes = p.tile_cap + kTileSlack, pk_bytes = 32u * p.words_per_read * 4u;
-	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * (raw_bytes + pk_bytes));
+	const uint32_t tile_bytes = 32u * p.words_per_read * 4u;
+	uint32_t *smem_counts = reinterpret_cast<uint32_t *>(dyn_smem + (size_t) kWarpsPerBlock * kTileBufs * tile_bytes);
 	const uint32_t G1 = p.n_genomes + 1, ncnt = 2 * G1;
 	if (p.smem_counters)
 		for (uint32_t i = tid; i < ncnt; i += blockDim.x)
@@ -326,8 +343,10 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 	if (tid < 2)
 		block_tot[tid] = 0;
 	WarpState &ws = warp_state[wib];
-	if (lane == 0)
-		mbarInit(&ws.bar, 1);
+	if (lane == 0) {
+		mbarInit(&ws.bar[0], 1);
+		mbarInit(&ws.bar[1], 1);
+	}
 	__syncthreads();
 
 	const uint32_t h = p.h;
@@ -335,138 +354,46 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 	const unsigned long long kmask = ~0ull >> (64 - 2 * h);
 	const uint32_t top_shift = 2 * h - 2;
 	const uint32_t lt_mask = (1u << lane) - 1u;
-	uint8_t *raw = dyn_smem + (size_t) wib * raw_bytes;
-	const uint32_t raw_addr = smemAddr(raw);
-	const uint32_t pk_warp = smemAddr(dyn_smem + (size_t) kWarpsPerBlock * raw_bytes + (size_t) wib * pk_bytes);
-	const uint32_t pk_mine = pk_warp + (uint32_t) lane * p.words_per_read * 4u;
+	uint8_t *tiles = dyn_smem + (size_t) wib * kTileBufs * tile_bytes;
+	const uint32_t tiles_addr = smemAddr(tiles);
 	const size_t warp_global = (size_t) blockIdx.x * kWarpsPerBlock + wib;
 	uint32_t *warp_spill = p.hit_spill + warp_global * 32 * p.spill_stride;
 	uint32_t *warp_set = p.dedup_sets + warp_global * p.dedup_slots;
 	uint32_t n_undet = 0, n_conf = 0, n_invalid = 0, n_probes = 0; // per lane (a lane sees < 2^32 / 512 reads per launch)
 	uint32_t n_cand = 0, n_leaf_hits = 0, n_chained = 0; // n_cand warp-uniform, the others per lane
-	uint32_t parity = 0;
+	uint32_t parity = 0; // bit b: phase of buffer b's mbarrier
 
 	const uint32_t n_sub = (uint32_t) ((p.n_reads + 31) / 32); // the host keeps a launch below 2^32 tiles
 	const uint32_t warp_stride = gridDim.x * kWarpsPerBlock;
 	uint32_t sub = blockIdx.x * kWarpsPerBlock + wib;
 
-	struct SubTile {
-		unsigned long long off; // this lane's read offset in the caller's base buffer
-		uint32_t lead;          // its offset inside the staged span (the span starts 16-byte aligned)
-		uint32_t rl, bytes;
-		bool have, staged;
-	};
-	// offsets / lengths of a tile's reads and the byte span they cover (warp-uniform)
-	auto describe = [&](uint32_t sub_idx) -> SubTile {
-		SubTile t;
-		const uint64_t r = (uint64_t) sub_idx * 32 + lane;
-		t.have = r < p.n_reads;
-		if (PACKED)
-			t.off = t.have ? (p.offsets32 ? (unsigned long long) p.offsets32[r] : p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
-		else
-			t.off = t.have ? (p.offsets ? p.offsets[r] : (p.read_base + r) * p.stride) : ~0ull;
-		t.rl = t.have ? p.lengths[r] : 0;
-		unsigned long long lo = t.off, hi = t.have ? t.off + (PACKED ? (t.rl + 3u) >> 2 : t.rl) : 0ull;
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			unsigned long long tl = __shfl_xor_sync(0xffffffffu, lo, o), th = __shfl_xor_sync(0xffffffffu, hi, o);
-			lo = tl < lo ? tl : lo;
-			hi = th > hi ? th : hi;
-		}
-		const unsigned long long start = lo & ~15ull;
-		t.bytes = hi > start ? (uint32_t) min((hi - start + 15ull) & ~15ull, 0xFFFFFFF0ull) : 0u;
-		t.staged = t.bytes > 0 && t.bytes <= p.tile_cap; // else: the reads are fetched from global directly
-		t.lead = t.staged && t.have ? (uint32_t) (t.off - start) : 0u;
-		return t;
-	};
-	// one bulk copy per tile; lane 0's read is the tile's first one only if offsets ascend, so the
-	// span start travels by shuffle from whichever lane holds the lowest offset
-	auto issueCopy = [&](const SubTile &t) {
-		if (!t.staged)
-			return;
-		const unsigned long long start = t.off - t.lead;
-		const uint32_t holders = __ballot_sync(0xffffffffu, t.have);
-		const unsigned long long span = __shfl_sync(0xffffffffu, start, __ffs(holders) - 1);
+	// one bulk copy per tile, straight into the layout the phases read
+	auto issueCopy = [&](uint32_t tile, uint32_t buf) {
 		if (lane == 0) {
-			mbarExpectTx(&ws.bar, t.bytes);
-			bulkCopyG2S(raw, p.bases + span, t.bytes, &ws.bar, pol_stream);
+			mbarExpectTx(&ws.bar[buf], tile_bytes);
+			bulkCopyG2S(tiles + buf * tile_bytes, p.words + (size_t) tile * 32 * p.words_per_read, tile_bytes, &ws.bar[buf], pol_stream);
 		}
 	};
 
-	if (sub < n_sub)
-		issueCopy(describe(sub));
-	for (; sub < n_sub; sub += warp_stride) {
-		// (the tile's offsets / lengths are re-read rather than carried in registers across a tile)
-		const SubTile cur = describe(sub);
-		if (cur.staged) {
-			mbarWait(&ws.bar, parity);
-			parity ^= 1u;
-		}
+	if (sub < n_sub && kTileBufs == 2)
+		issueCopy(sub, 0);
+	for (uint32_t it = 0; sub < n_sub; sub += warp_stride, it++) {
+		const uint32_t buf = kTileBufs == 2 ? (it & 1u) : 0u;
+		// the other buffer is free (its tile was finished one iteration ago): the next tile's words
+		// arrive while this tile is scanned
+		if (kTileBufs == 2) {
+			if (sub + warp_stride < n_sub)
+				issueCopy(sub + warp_stride, buf ^ 1u);
+		} else
+			issueCopy(sub, 0);
 		const uint64_t r = (uint64_t) sub * 32 + lane;
-		const bool have = cur.have, staged = cur.staged;
-		const uint32_t rl = cur.rl;
-		const uint32_t wmax = __reduce_max_sync(0xffffffffu, rl);
+		const bool have = r < p.n_reads;
+		const uint32_t rl = have ? p.lengths[r] : 0u;
+		mbarWait(&ws.bar[buf], (parity >> buf) & 1u);
+		parity ^= 1u << buf;
+		const uint32_t pk_warp = tiles_addr + buf * tile_bytes;
 
-		// ---- stage: lane r packs read r, 16 bases per word, first base in the top bits -------------
-		uint32_t bad = 0;
-		{
-			const uint32_t src = raw_addr + cur.lead;
-			const uint8_t *gsrc = p.bases + (have ? cur.off : 0ull);
-			const uint32_t n_words = (wmax + 15u) >> 4;
-			for (uint32_t c = 0; c < n_words; c++) {
-				const int n = (int) rl - (int) (16u * c); // bases of this read in word c
-				uint32_t word = 0;
-				if (n > 0) {
-					if (PACKED) {
-						// four bytes of the host-packed read = this word, big-endian (validated by the host)
-						uint32_t v = 0;
-						if (staged) {
-							const uint32_t a = src + 4u * c;
-							v = __funnelshift_r(ldsU32(a & ~3u), ldsU32((a & ~3u) + 4u), (a & 3u) * 8u);
-						} else {
-							const uint32_t nb = min(4u, ((uint32_t) n + 3u) >> 2);
-							for (uint32_t t = 0; t < nb; t++)
-								v |= (uint32_t) gsrc[4u * c + t] << (8u * t);
-						}
-						word = __byte_perm(v, 0u, 0x0123);
-					} else {
-						uint32_t d[4] = {0u, 0u, 0u, 0u};
-						if (staged) {
-							const uint32_t a = src + 16u * c, al = a & ~3u, sh = (a & 3u) * 8u;
-							uint32_t w[5];
-#pragma unroll
-							for (int t = 0; t < 5; t++)
-								w[t] = ldsU32(al + 4u * t);
-#pragma unroll
-							for (int t = 0; t < 4; t++)
-								d[t] = __funnelshift_r(w[t], w[t + 1], sh);
-						} else {
-							const uint32_t nb = min(16u, (uint32_t) n);
-							for (uint32_t t = 0; t < nb; t++)
-								d[t >> 2] |= (uint32_t) gsrc[16u * c + t] << (8u * (t & 3u));
-						}
-#pragma unroll
-						for (int t = 0; t < 4; t++) {
-							// codes A/a=0 C/c=1 G/g=2 T/t=3 (query.cpp:1860-1883) in each byte; validity: fold
-							// case and compare with the letter each code stands for (one byte permute)
-							const uint32_t t4 = (d[t] >> 1) & 0x03030303u;
-							const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-							const uint32_t nib = code4 | (code4 >> 4);
-							const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-							const int left = n - 4 * t;
-							const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
-							bad |= ((d[t] & 0xDFDFDFDFu) ^ expect4) & live;
-							// four 2-bit codes -> one byte, first base in the top bits
-							word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
-						}
-					}
-					if (n < 16)
-						word &= 0xFFFFFFFFu << (32 - 2 * n);
-				}
-				asm volatile("st.shared.u32 [%0], %1;" ::"r"(pk_mine + 4u * c), "r"(word) : "memory");
-			}
-		}
-		const bool valid = have && bad == 0 && rl >= h;
+		const bool valid = have && rl >= h; // invalid reads arrive with length 0
 		const uint32_t npos = valid ? rl - h + 1 : 0;
 		// strips of the tile, flattened over its reads
 		const uint32_t my_strips = (npos + kStrip - 1) / kStrip;
@@ -487,9 +414,6 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 		const uint32_t strip_inv = uniform_strips ? (65536u + my_strips - 1) / my_strips : 0u;
 		n_probes += 2 * npos; // both strands of every window
 		__syncwarp();
-		// the raw buffer is free: the next tile's bytes arrive while this one is scanned
-		if (sub + warp_stride < n_sub)
-			issueCopy(describe(sub + warp_stride));
 
 		// ---- phase 1: a strip of kStrip positions per lane, all probes in flight before any test ---
 		uint32_t nq = 0; // queue fill, warp-uniform
@@ -544,8 +468,11 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 					kf[t] = hf;
 					bk0[t] = bk1[t] = 0ull;
 					// a key and its reverse complement share their home bucket: one sector per position
-					if ((uint32_t) t < count)
-						loadBucketKeys(p.table + (mixKey(hf < hr ? hf : hr) & p.table_mask), bk0[t], bk1[t]);
+					if ((uint32_t) t < count) {
+						uint32_t A;
+						filterHash(hf < hr ? hf : hr, A, bsel[t]);
+						loadBucketKeys(p.table + tableBucket(bsel[t], p.table_shift), bk0[t], bk1[t]);
+					}
 				}
 			}
 #pragma unroll
@@ -567,20 +494,24 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 				const uint32_t strands = (cand_f ? 1u : 0u) | (cand_r ? 2u : 0u);
 				const uint32_t m = __ballot_sync(0xffffffffu, strands != 0);
 				if (m) { // warp-uniform; the queue slot of a lane is its rank among the lanes with a candidate
-					if (strands)
+					if (strands) {
 						ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) ((slot << 10) | (strands << 8) | (i0 + t));
+						// the candidate's bucket travels from HBM to L2 while the rest of the tile is probed
+						if (FILTER)
+							prefetchL2(p.table + tableBucket(bsel[t], p.table_shift));
+					}
 					nq += __popc(m);
 				}
 			}
 			// a round adds at most 32 * kStrip entries: drain above half
 			if (nq > (uint32_t) (kQueueCap - 32 * kStrip)) {
 				n_cand += nq;
-				drainQueue(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+				drainQueue<MODE>(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
 				nq = 0;
 			}
 		}
 		n_cand += nq;
-		drainQueue(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+		drainQueue<MODE>(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
 
 		// ---- phase 3: lane r: leaf set of read r -> decision (query.cpp:529-636) -------------------
 		uint32_t cls = CQ_CLASS_UNLABELED, rid_a = 0, rid_b = 0, distinct_u = 0, distinct_d = 0;
@@ -790,6 +721,91 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 	}
 	if (tid < 2 && block_tot[tid])
 		atomicAdd(&p.counts[ncnt + tid], block_tot[tid]);
+}
+
+// ------------------------------------------------------------------- read packing (A1)
+//
+// One thread per (read, word): 16 bases -> one 32-bit word of the scan's tile layout.  ASCII input
+// is what query64_* consumes (one byte per base, any alignment): decoded with the codes of
+// query.cpp:1860-1883, validated (a byte outside ACGTacgt zeroes the read's length: the read is
+// then counted unlabeled and invalid), packed first base most significant.  PACKED_IN: the bytes
+// the host packer / FASTQ reader produce (four bases per byte, validated there) are regrouped into
+// words.  Reads past n_reads up to a whole tile are written as zeros.
+struct PackParams {
+	const uint8_t *bases;
+	const uint64_t *offsets;   // NULL: read i starts at (read_base + i) * stride
+	const uint32_t *offsets32; // PACKED_IN only: 32-bit offsets, or NULL
+	uint64_t stride, read_base;
+	const uint8_t *lengths_in;
+	uint64_t n_reads, n_padded; // n_padded = n_reads rounded up to 32
+	uint32_t words_per_read;
+	uint32_t *words;           // [n_padded][words_per_read]
+	uint8_t *lengths_out;      // ASCII input: a copy of lengths_in in which invalid reads are zeroed
+};
+
+__device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
+	uint32_t v;
+	asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(a));
+	return v;
+}
+
+template <bool PACKED_IN>
+__global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
+	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t r = idx / q.words_per_read;
+	const uint32_t c = (uint32_t) (idx - r * q.words_per_read);
+	if (r >= q.n_padded)
+		return;
+	uint32_t word = 0;
+	if (r < q.n_reads) {
+		const int n = (int) q.lengths_in[r] - (int) (16u * c); // bases of this read in word c
+		if (n > 0) {
+			unsigned long long off;
+			if (PACKED_IN)
+				off = q.offsets32 ? (unsigned long long) q.offsets32[r] : q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
+			else
+				off = q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
+			if (PACKED_IN) {
+				// four bytes of the host-packed read = this word, big-endian; bytes past the read are masked
+				const uint8_t *a = q.bases + off + 4u * c;
+				const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
+				const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
+				const uint32_t w0 = ldgU32(al), w1 = sh ? ldgU32(al + 4) : 0u; // an aligned word never needs the next one
+				word = __byte_perm(__funnelshift_r(w0, w1, sh), 0u, 0x0123);
+			} else {
+				// sixteen ASCII bytes at any alignment: five aligned words, funnel-shifted
+				const uint8_t *a = q.bases + off + 16u * c;
+				const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
+				const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
+				const uint32_t nw = ((uint32_t) ((uintptr_t) a & 3u) + (uint32_t) min(n, 16) + 3u) >> 2; // aligned words the bases touch
+				uint32_t w[5];
+#pragma unroll
+				for (int t = 0; t < 5; t++)
+					w[t] = (uint32_t) t < nw ? ldgU32(al + 4 * t) : 0u;
+				uint32_t bad = 0;
+#pragma unroll
+				for (int t = 0; t < 4; t++) {
+					const uint32_t d = __funnelshift_r(w[t], w[t + 1], sh);
+					// codes A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
+					// letter each code stands for (one byte permute)
+					const uint32_t t4 = (d >> 1) & 0x03030303u;
+					const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+					const uint32_t nib = code4 | (code4 >> 4);
+					const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+					const int left = n - 4 * t;
+					const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
+					bad |= ((d & 0xDFDFDFDFu) ^ expect4) & live;
+					// four 2-bit codes -> one byte, first base in the top bits
+					word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
+				}
+				if (bad)
+					q.lengths_out[r] = 0; // every thread of an invalid read that sees a bad byte stores the same 0
+			}
+			if (n < 16)
+				word &= 0xFFFFFFFFu << (32 - 2 * n);
+		}
+	}
+	q.words[idx] = word;
 }
 
 // counts[i] += sum over blocks of partials[b][i]; one thread per counter, coalesced over i.

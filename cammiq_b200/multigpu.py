@@ -20,11 +20,17 @@ def combine_counters(counts, rcount_u=None, rcount_d=None, dst=0, group=None):
     is bit-identical to the unsigned sums.  No-op without an initialised process group."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    dist.reduce(counts, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    if rcount_u is not None and rcount_u.numel() > 0:
-        dist.reduce(rcount_u, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    if rcount_d is not None and rcount_d.numel() > 0:
-        dist.reduce(rcount_d, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    tensors = [counts] + [t for t in (rcount_u, rcount_d) if t is not None and t.numel() > 0]
+    grouped = getattr(dist, "_coalescing_manager", None)
+    if counts.is_cuda and len(tensors) > 1 and grouped is not None:
+        # ONE grouped NCCL launch for the whole exchange (ncclGroupStart/End around the three sums);
+        # the coalescing manager groups all-reduces, which leaves the totals on rank `dst` as well
+        with grouped(group=group, device=counts.device):
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return
+    for t in tensors:
+        dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
 
 
 def gather_pair_maps(pairs, dst=0, group=None):

@@ -323,6 +323,15 @@ int cq_reads_stage(cq_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, u
 int cq_reads_stage_packed(cq_ctx *ctx, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads);
 int cq_query_staged(cq_ctx *ctx, int mode);
+/* cq_query / cq_query_packed without the copy of the totals to the host: the reads flow through the
+   same pack -> copy -> scan pipeline from HOST buffers and the results stay in the device
+   accumulators (for launchers that combine the accumulators of several processes with their own
+   collective first and fetch the reduced totals once, on one rank).  Returns when every chunk
+   has been submitted; the caller's read buffers are free again after cq_sync. */
+int cq_query_submit(cq_ctx *ctx, int mode, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads);
+int cq_query_submit_packed(cq_ctx *ctx, int mode, const uint8_t *packed, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t n_reads);
 int cq_sync(cq_ctx *ctx);
 /* Copy the accumulated totals to host buffers (same semantics as cq_query's out). */
 int cq_fetch(cq_ctx *ctx, int mode, cq_result *out);

@@ -18,7 +18,15 @@
  *   ref_harness time <idx_u> <idx_d> <map> <p|mt|sc> <nthreads> <fastq> [reps]
  *       prints one JSON line per repetition (the reference's own scan, timed around the
  *       query64_* call like its "Time for query" bracket) and leaves with _exit so that the
- *       pointer-trie teardown (tens of seconds at 3e7 leaves) is not waited for
+ *       pointer-trie teardown (tens of seconds at 3e7 leaves) is not waited for.  The line
+ *       carries the full per-genome vectors (cu, cd), the pair map (sc) and, for the per-leaf
+ *       counts, sum and a position-weighted digest over Hash::map_sp in its own order:
+ *       sum over g, k of rcount(map_sp[g][k]) * mix64(g << 32 | k)  (mod 2^64)
+ *   ref_harness ilp <idx_u> <idx_d> <map> <erate> <out> <fastq>
+ *       query64_p, then what runILP_* derives per leaf before it builds the model, evaluated
+ *       with the expressions of query.cpp:1087, 1157-1160, 1171-1175 on the reference's own
+ *       nodes (the solver code itself is compiled out without CPLEX / Gurobi): one line
+ *       "<U|D> <genome> <k> <rcount> <wcov1 %.17g> <wcov2 %.17g>" per map_sp entry
  *
  *   ref_harness readdump <fastq> <min_len>
  *       what FqReader::readFastq (query.cpp:371-425) holds after reading the file: one line
@@ -32,6 +40,7 @@
  */
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -129,6 +138,26 @@ static void readLeafSets(FqReader &fq, uint8_t *read, size_t rl, std::set<pleafN
 	}
 }
 
+static uint64_t mix64(uint64_t x) {
+	x += 0x9E3779B97F4A7C15ull;
+	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+	x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+	return x ^ (x >> 31);
+}
+
+static void rcountDigest(Hash *ht, size_t G, uint64_t &sum, uint64_t &digest) {
+	sum = digest = 0;
+	for (size_t rid = 1; rid <= G; rid++) {
+		auto it = ht->map_sp.find((uint32_t) rid);
+		if (it == ht->map_sp.end())
+			continue;
+		for (size_t k = 0; k < it->second.size(); k++) {
+			sum += it->second[k]->rcount;
+			digest += (uint64_t) it->second[k]->rcount * mix64(((uint64_t) rid << 32) | (uint64_t) k);
+		}
+	}
+}
+
 static void runQuery(FqReader &fq, const std::string &mode, size_t fi) {
 	if (mode == "p")
 		fq.query64_p(fi);
@@ -156,9 +185,53 @@ static int readDump(const std::string &fastq, size_t min_len) {
 	_exit(0);
 }
 
+static void ilpLeaves(FILE *out, const char *tag, Hash *ht, size_t G, uint32_t rl, double erate) {
+	for (size_t i = 0; i < G; i++) {
+		auto it = ht->map_sp.find((uint32_t) (i + 1));
+		if (it == ht->map_sp.end())
+			continue;
+		size_t k = 0;
+		for (auto pn : it->second) {
+			/* the expressions of query.cpp:1157-1160 (unique) and 1171-1175 (doubly unique), verbatim */
+			double wcov1 = (pn->ucount1 * (rl - pn->depth) * 1.0 / rl);
+			double wcov2 = (pn->ucount2 * (rl - pn->depth) * 1.0 / rl);
+			wcov1 = wcov1 * pow(1 - erate, pn->depth);
+			wcov2 = wcov2 * pow(1 - erate, pn->depth);
+			fprintf(out, "%s %zu %zu %u %.17g %.17g\n", tag, i + 1, k++, pn->rcount, wcov1, wcov2);
+		}
+	}
+}
+
+static int ilpDump(int argc, char **argv) {
+	std::string idx_u = argv[2], idx_d = argv[3], map_fn = argv[4], out_fn = argv[6], fastq = argv[7], empty;
+	float erate_f = (float) atof(argv[5]); /* FqReader keeps -e as a float (query.hpp:62) */
+	(void) argc;
+	FqReader fq(idx_u, idx_d, map_fn, empty, erate_f, false);
+	fq.loadIdx_p();
+	fq.loadSmap();
+	fq.qfilenames.push_back(fastq);
+	fq.prepallFastq();
+	fq.readallFastq();
+	fq.getFqnameWithoutDir(0);
+	fq.query64_p(0);
+	FILE *out = fopen(out_fn.c_str(), "w");
+	if (out == NULL)
+		return 1;
+	size_t G = fq.genomes.size() - 1;
+	uint32_t rl = fq.tlengths[0] / fq.reads[0].size(); /* query.cpp:1087 */
+	double erate = fq.erate_;                          /* the double parameter of runILP_* (query.cpp:252) */
+	fprintf(out, "RL %u\n", rl);
+	ilpLeaves(out, "U", fq.ht_u, G, rl, erate);
+	ilpLeaves(out, "D", fq.ht_d, G, rl, erate);
+	fclose(out);
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	if (argc == 4 && std::string(argv[1]) == "readdump")
 		return readDump(argv[2], (size_t) atol(argv[3]));
+	if (argc == 8 && std::string(argv[1]) == "ilp")
+		return ilpDump(argc, argv);
 	if (argc < 8) {
 		fprintf(stderr, "usage: see header of oracle/ref_harness.cpp\n");
 		return 2;
@@ -212,9 +285,30 @@ int main(int argc, char **argv) {
 				sd += fq.genomes[i]->read_cnts_d;
 			}
 			printf("{\"rep\": %d, \"reads\": %zu, \"query_ms\": %.3f, \"load_ms\": %.3f, \"threads\": %d, "
-				"\"mode\": \"%s\", \"nundet\": %zu, \"nconf\": %zu, \"sum_u\": %lu, \"sum_d\": %lu}\n",
+				"\"mode\": \"%s\", \"nundet\": %zu, \"nconf\": %zu, \"sum_u\": %lu, \"sum_d\": %lu",
 				rep, fq.reads[0].size(), q_ms, load_ms, nthreads, mode.c_str(), fq.nundet, fq.nconf,
 				(unsigned long) su, (unsigned long) sd);
+			printf(", \"cu\": [");
+			for (size_t i = 1; i <= G; i++)
+				printf(i < G ? "%lu, " : "%lu", (unsigned long) fq.genomes[i]->read_cnts_u);
+			printf("], \"cd\": [");
+			for (size_t i = 1; i <= G; i++)
+				printf(i < G ? "%lu, " : "%lu", (unsigned long) fq.genomes[i]->read_cnts_d);
+			printf("]");
+			if (mode != "sc") {
+				uint64_t s1, d1, s2, d2;
+				rcountDigest(fq.ht_u, G, s1, d1);
+				rcountDigest(fq.ht_d, G, s2, d2);
+				printf(", \"rcu_sum\": %lu, \"rcu_digest\": \"%016lx\", \"rcd_sum\": %lu, \"rcd_digest\": \"%016lx\"",
+					(unsigned long) s1, (unsigned long) d1, (unsigned long) s2, (unsigned long) d2);
+			} else {
+				printf(", \"pairs\": [");
+				size_t k = 0;
+				for (auto &it : fq.read_cnts_b)
+					printf(k++ ? ", [%u, %u, %lu]" : "[%u, %u, %lu]", it.first.first, it.first.second, (unsigned long) it.second);
+				printf("]");
+			}
+			printf("}\n");
 			fflush(stdout);
 			if (rep + 1 < reps) {
 				if (mode == "sc") fq.resetCounters_sc();

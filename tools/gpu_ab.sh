@@ -9,7 +9,7 @@ python tools/kernel_ab.py > $out/ab_main.json 2> $out/ab_main.err
 echo "main rc=$?"; cat $out/ab_main.json
 timeout 1200 python -m pytest tests -m gpu -x -q > $out/gputests.log 2>&1
 echo "tests rc=$?"; tail -5 $out/gputests.log
-for v in s8b3 s8b3a s8b2 s4b3 s4b4; do
+for v in s8b3 s8b4 s8b2 s4b4; do
   CAMMIQ_LIB=$PWD/cammiq_b200/variants/libcammiq_gpu_$v.so python tools/kernel_ab.py >> $out/ab_variants.jsonl 2>> $out/ab_variants.err
 done
 cat $out/ab_variants.jsonl
@@ -20,7 +20,7 @@ python tools/kernel_ab.py --filter-mb 32 >> $out/ab_more.jsonl 2>> $out/ab_more.
 python tools/kernel_ab.py --filter-mb 48 >> $out/ab_more.jsonl 2>> $out/ab_more.err
 python tools/kernel_ab.py --mode sc >> $out/ab_more.jsonl 2>> $out/ab_more.err
 cat $out/ab_more.jsonl
-ncu --set full --import-source on --clock-control none -k regex:scan_reads -s 2 -c 1 -o $out/scan_full python tools/kernel_ab.py --iters 1 > $out/ncu.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:scan_reads -c 1 -o $out/scan_full python tools/kernel_ab.py --iters 1 > $out/ncu.log 2>&1
 echo "ncu rc=$?"
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:scan_reads -s 2 -c 1 --csv --log-file $out/ncu_f32.csv python tools/kernel_ab.py --iters 1 --filter-mb 32 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_f32.csv python tools/kernel_ab.py --iters 1 --filter-mb 32 > /dev/null 2>&1
 ls -la $out

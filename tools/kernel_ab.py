@@ -48,7 +48,7 @@ def main():
     else:
         ctx.stage(reads.reshape(-1), None, lengths, stride=rl)
     mode = cq.MODE_P if a.mode == "p" else cq.MODE_SC
-    ms = []
+    ms, pk = [], []
     warm = 0 if a.iters <= 1 else 40   # ~0.3 s of launches: clocks and power state settle before timing
     for i in range(a.iters + warm):
         ctx.reset()
@@ -59,6 +59,7 @@ def main():
             ctx.sync()
             t = ctx.timing()
             ms.append(t["scan_ms_sum"])
+            pk.append(t["pack_ms_sum"])
     r = ctx.fetch(mode)
     chk = [int(r["nundet"]), int(r["nconf"]), int(r["cnt_u"].sum()), int(r["cnt_d"].sum())]
     if mode == cq.MODE_P:
@@ -66,7 +67,7 @@ def main():
                 int((r["rcount_u"].astype(np.uint64) * (np.arange(len(r["rcount_u"]), dtype=np.uint64) % 1000003)).sum())]
     print(json.dumps({"lib": os.path.basename(cq.capi.library_path()), "workload": a.workload, "reads": n, "read_len": rl,
                       "packed": a.packed, "filter_mb": idx.info.filter_bytes / (1 << 20),
-                      "scan_ms_mean": float(np.mean(ms)), "scan_ms_min": float(np.min(ms)),
+                      "scan_ms_mean": float(np.mean(ms)), "scan_ms_min": float(np.min(ms)), "pack_ms_mean": float(np.mean(pk)),
                       "reads_per_s": n / (float(np.mean(ms)) * 1e-3),
                       "regs": t["regs_per_thread"], "grid": t["grid_blocks"], "blocks_per_sm": t["blocks_per_sm"],
                       "dyn_smem": t["dyn_smem_bytes"], "probes": t["probes"], "candidates": t["bucket_hits"],
