@@ -108,12 +108,18 @@ def make_reads(w, first, n, out=None):
     from cammiq_b200 import synthlib as sl
     reads = sl.make_reads(synth_params(w), first, n, w["read_len"], w["erate"], out=out)
     if w.get("n_rate", 0) > 0:
-        rng = np.random.default_rng(w["seed"] * 1000003 + first)
-        n_n = rng.binomial(reads.size, w["n_rate"])
-        pos = rng.integers(0, reads.size, n_n)
-        sub = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, reads.shape[0])]
-        flat = reads.reshape(-1)
-        flat[pos] = sub[pos // w["read_len"]]
+        # per block of 65536 reads, seeded by the block number: the same read gets the same N
+        # positions and the same substitute whatever range it is generated in
+        rl, blk = w["read_len"], 65536
+        alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+        for b in range(first // blk, (first + n + blk - 1) // blk):
+            rng = np.random.default_rng([w["seed"], 7919, b])
+            mask = rng.random((blk, rl)) < w["n_rate"]
+            sub = alpha[rng.integers(0, 4, blk)]
+            lo, hi = max(first, b * blk), min(first + n, (b + 1) * blk)
+            m = mask[lo - b * blk:hi - b * blk]
+            view = reads[lo - first:hi - first]
+            view[m] = np.broadcast_to(sub[lo - b * blk:hi - b * blk, None], m.shape)[m]
     return reads
 
 
@@ -327,19 +333,21 @@ def profiled_counters(name):
     return t.get(name), None
 
 
-def gather_peak(ctx, region_bytes, smem_per_block=0, blocks_per_sm=8):
+def gather_peak(ctx, region_bytes, smem_per_block=0, blocks_per_sm=8, carveout_pct=None):
     """Random 8-byte gathers over an L2-sized region (what the filter probes are), optionally with
-    the shared-memory footprint of the scan kernel taken out of each SM's L1."""
+    the shared-memory footprint and carve-out of the scan kernel taken out of each SM's L1."""
     r = 1 << 20
     while r < region_bytes:
         r <<= 1
     os.environ["CAMMIQ_GATHER_SMEM"] = str(int(smem_per_block))
     os.environ["CAMMIQ_GATHER_BLOCKS"] = str(int(blocks_per_sm))
+    if carveout_pct is not None:
+        os.environ["CAMMIQ_GATHER_CARVEOUT"] = str(int(carveout_pct))
     try:
         return ctx.bench_random_gather(r, 8, 1 << 27, iters=2)
     finally:
-        os.environ.pop("CAMMIQ_GATHER_SMEM", None)
-        os.environ.pop("CAMMIQ_GATHER_BLOCKS", None)
+        for k in ("CAMMIQ_GATHER_SMEM", "CAMMIQ_GATHER_BLOCKS", "CAMMIQ_GATHER_CARVEOUT"):
+            os.environ.pop(k, None)
 
 
 def timed_scan(ctx, mode, steps, warmup):
@@ -815,12 +823,14 @@ def run(json_fd):
         fr = {}
         if has_filter:
             # one filter word (L2) per read position: the measured L2 random-gather rate is the roofline
-            smem_block = stats["dyn_smem_bytes"] + 14 * 1024 + 1024
+            pct = stats["smem_carveout_pct"]
+            smem_block = pct * 228 * 1024 // 100 // max(stats["blocks_per_sm"], 1) - 1024
             g_free = gather_peak(ctx, info.filter_bytes)
-            g_kernel = gather_peak(ctx, info.filter_bytes, smem_per_block=smem_block, blocks_per_sm=stats["blocks_per_sm"])
+            g_kernel = gather_peak(ctx, info.filter_bytes, smem_per_block=smem_block, blocks_per_sm=stats["blocks_per_sm"],
+                                   carveout_pct=pct)
             rate = positions / (scan_ms * 1e-3) / 1e9
             fr["l2_gather"] = {"filter_loads_g_per_s": rate, "peak_g_per_s": g_kernel, "frac": rate / g_kernel,
-                               "peak_whole_l1_g_per_s": g_free,
+                               "peak_whole_l1_g_per_s": g_free, "smem_carveout_pct": pct,
                                "note": "peak = cq_bench_random_gather over a region of the filter's size, same run, with the scan "
                                        "kernel's shared-memory footprint taken out of each SM's L1 (in-flight gathers live in L1)"}
         else:

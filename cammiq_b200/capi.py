@@ -38,6 +38,7 @@ class IndexInfo(C.Structure):
     _fields_ = [("hash_len", C.c_uint32), ("n_leaves_u", C.c_uint64), ("n_leaves_d", C.c_uint64),
                 ("n_buckets_u", C.c_uint64), ("n_buckets_d", C.c_uint64), ("n_keys", C.c_uint64),
                 ("n_table_buckets", C.c_uint64), ("n_nodes_u", C.c_uint64), ("n_nodes_d", C.c_uint64),
+                ("n_cnodes_u", C.c_uint64), ("n_cnodes_d", C.c_uint64),
                 ("max_ref_id", C.c_uint32), ("filter_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("decode_ms", C.c_double), ("flatten_ms", C.c_double)]
 
@@ -81,7 +82,7 @@ class Timing(C.Structure):
                 ("pack_ms_sum", C.c_double), ("scan_ms_sum", C.c_double), ("reduce_ms_sum", C.c_double),
                 ("steps", C.c_uint64), ("grid_blocks", C.c_uint32), ("blocks_per_sm", C.c_uint32),
                 ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32),
-                ("host_pack_ms", C.c_double), ("host_pack_threads", C.c_uint32), ("reserved0", C.c_uint32),
+                ("host_pack_ms", C.c_double), ("host_pack_threads", C.c_uint32), ("smem_carveout_pct", C.c_uint32),
                 ("h2d_bytes", C.c_uint64)]
 
 

@@ -90,6 +90,8 @@ extern "C" int cq_index_get_info(const cq_index *idx, cq_index_info *info) {
 	info->n_table_buckets = f.n_table_buckets;
 	info->n_nodes_u = f.u.numNodes();
 	info->n_nodes_d = f.d.numNodes();
+	info->n_cnodes_u = f.cnodes_u.size() / 4;
+	info->n_cnodes_d = f.cnodes_d.size() / 4;
 	info->max_ref_id = std::max(f.u.max_ref_id, f.d.max_ref_id);
 	info->filter_bytes = f.filter.size() * 8;
 	info->device_bytes = f.deviceBytes();
@@ -345,8 +347,8 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	Uploader up(c->stream);
 	if ((rc = uploadArray(&c->d_table, f.table.data(), f.table.size(), up)) != 0) return rc;
 	lap("prefix table");
-	if ((rc = uploadArray(&c->d_nodes_u, f.u.nodes.data(), f.u.nodes.size(), up)) != 0) return rc;
-	if ((rc = uploadArray(&c->d_nodes_d, f.d.nodes.data(), f.d.nodes.size(), up)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_u, f.cnodes_u.data(), f.cnodes_u.size(), up)) != 0) return rc;
+	if ((rc = uploadArray(&c->d_nodes_d, f.cnodes_d.data(), f.cnodes_d.size(), up)) != 0) return rc;
 	if ((rc = uploadArray(&c->d_leaf_u_ref, f.u.ref_id1.data(), f.u.ref_id1.size(), up)) != 0) return rc;
 	FlatVec<uint2>::type dref(f.d.numLeaves());
 	up.pool.run([&](int t) {
@@ -373,10 +375,14 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	if (!f.filter.empty()) {
 		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), up)) != 0) return rc;
 		c->filter_words = f.filter_words;
+		c->filter_sel = f.filter_sel_mask;
+		c->filter_sieve = f.filter_sieve;
 		CQ_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	// block-private genome counters in shared memory when they fit, global atomics otherwise;
 	// the grid itself is sized per launch (it depends on the tile's shared-memory footprint)
+	// (a large counter block would eat the L1 the in-flight probes need: beyond kMaxSmemGenomes the
+	// warps' match_any-combined adds go to global memory instead)
 	c->smem_counters = n_genomes <= kMaxSmemGenomes;
 	c->smem_bytes = c->smem_counters ? ncnt * sizeof(uint32_t) : 0;
 	c->max_grid = kMaxBlocksPerSM * c->n_sms;
@@ -527,8 +533,9 @@ static int launchPack(cq_ctx *c, const ReadBatch &rb) {
 		CQ_CUDA(cudaMemcpyAsync(c->d_len2[s], rb.lengths, rb.n, cudaMemcpyDeviceToDevice, c->stream));
 		q.lengths_out = c->d_len2[s];
 	}
-	const uint64_t threads = q.n_padded * q.words_per_read;
-	const unsigned blocks = (unsigned) ((threads + 255) / 256);
+	q.reads_per_block = 256 / q.words_per_read;
+	q.inv_words = (65536 + q.words_per_read - 1) / q.words_per_read;
+	const unsigned blocks = (unsigned) ((q.n_padded + q.reads_per_block - 1) / q.reads_per_block);
 	if (rb.packed)
 		pack_tiles_kernel<true><<<blocks, 256, 0, c->stream>>>(q);
 	else
@@ -555,6 +562,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.n_genomes = c->n_genomes;
 	sp.filter = c->d_filter;
 	sp.filter_words = c->filter_words;
+	sp.filter_sel = c->filter_sel;
 	sp.words = c->d_words[rb.slot];
 	sp.lengths = rb.packed ? rb.lengths : c->d_len2[rb.slot];
 	sp.n_reads = rb.n;
@@ -602,11 +610,12 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 		sp.read_leaf_u = c->d_leaf_u + rb.first * c->leaf_cap;
 		sp.read_leaf_d = c->d_leaf_d + rb.first * c->leaf_cap;
 	}
-	const bool filt = c->d_filter != NULL;
-	static const void *const kernels[4] = {
-		(const void *) scan_reads_kernel<CQ_MODE_P, false>, (const void *) scan_reads_kernel<CQ_MODE_P, true>,
-		(const void *) scan_reads_kernel<CQ_MODE_SC, false>, (const void *) scan_reads_kernel<CQ_MODE_SC, true>};
-	const int variant = mode * 2 + (filt ? 1 : 0);
+	const int filt = c->d_filter == NULL ? 0 : c->filter_sieve ? 2 : 1;
+	static const void *const kernels[6] = {
+		(const void *) scan_reads_kernel<CQ_MODE_P, 0>, (const void *) scan_reads_kernel<CQ_MODE_P, 1>,
+		(const void *) scan_reads_kernel<CQ_MODE_P, 2>, (const void *) scan_reads_kernel<CQ_MODE_SC, 0>,
+		(const void *) scan_reads_kernel<CQ_MODE_SC, 1>, (const void *) scan_reads_kernel<CQ_MODE_SC, 2>};
+	const int variant = mode * 3 + filt;
 	const void *kern = kernels[variant];
 	if (dyn_smem != c->last_dyn_smem[variant]) {
 		CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_smem));
@@ -635,7 +644,9 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 			pct = atoi(getenv("CAMMIQ_CARVEOUT"));
 		if (pct >= 0)
 			CQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+		c->last_carveout[variant] = pct;
 	}
+	c->timing.smem_carveout_pct = (uint32_t) std::max(0, c->last_carveout[variant]);
 	const uint64_t n_tiles = (rb.n + kScanThreads - 1) / kScanThreads; // one 32-read sub-tile per warp at least
 	c->grid = (int) std::min<uint64_t>((uint64_t) c->last_per_sm[variant] * c->n_sms, n_tiles);
 	c->timing.grid_blocks = (uint32_t) c->grid;
@@ -1260,6 +1271,13 @@ extern "C" int cq_bench_random_gather(cq_ctx *c, uint64_t region_bytes, int acce
 	const size_t dsm = getenv("CAMMIQ_GATHER_SMEM") ? (size_t) atol(getenv("CAMMIQ_GATHER_SMEM")) : 0;
 	const int per_sm = getenv("CAMMIQ_GATHER_BLOCKS") ? std::max(1, atoi(getenv("CAMMIQ_GATHER_BLOCKS"))) : 8;
 	const int grid = c->n_sms * per_sm;
+	if (getenv("CAMMIQ_GATHER_CARVEOUT")) {
+		const int pct = atoi(getenv("CAMMIQ_GATHER_CARVEOUT"));
+		cudaFuncSetAttribute((const void *) random_gather_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute((const void *) random_gather_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+	}
 	if (dsm > 0) {
 		cudaFuncSetAttribute((const void *) random_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);
 		cudaFuncSetAttribute((const void *) random_gather_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsm);

@@ -59,7 +59,8 @@ struct cq_ctx {
 	uint32_t *d_dedup = NULL; // hash-set scratch of the cooperative leaf dedup, [max grid warps][dedup_slots]
 	size_t cap_spill = 0, cap_dedup = 0;
 	uint2 *d_filter = NULL;
-	uint32_t filter_words = 0;
+	uint32_t filter_words = 0, filter_sel = 0x77777777u;
+	bool filter_sieve = false;
 	int max_grid = 0;
 	unsigned long long *d_probe_count = NULL;
 	int grid = 0;
@@ -75,8 +76,9 @@ struct cq_ctx {
 	uint32_t staged_max_len = 0;
 	uint64_t staged_shift = 0; // offset of d_bases[0] in the caller's base buffer
 	bool staged_packed = false;
-	size_t last_dyn_smem[4] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
-	int last_per_sm[4] = {0, 0, 0, 0};
+	size_t last_dyn_smem[6] = {(size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1, (size_t) -1}; // per kernel variant
+	int last_per_sm[6] = {0, 0, 0, 0, 0, 0};
+	int last_carveout[6] = {0, 0, 0, 0, 0, 0};
 	// host->device pipeline of cq_query: kStages chunk buffers rotate through copy and scan
 	static const int kStages = 3;
 	cudaStream_t copy_stream = NULL;

@@ -13,7 +13,7 @@
 namespace cammiq {
 
 uint64_t FlatIndex::deviceBytes() const {
-	return table.size() * sizeof(TableBucket) + filter.size() * 8 + (u.nodes.size() + d.nodes.size()) * 4 +
+	return table.size() * sizeof(TableBucket) + filter.size() * 8 + (cnodes_u.size() + cnodes_d.size()) * 4 +
 		u.numLeaves() * 4 + d.numLeaves() * 8 + (u.numLeaves() + d.numLeaves()) * 4;
 }
 
@@ -64,6 +64,98 @@ inline SlotRef probeInsert(RawArray<TableBucket> &t, uint64_t mask, uint32_t shi
 	}
 }
 
+// ---- path compression of the decoded tries ------------------------------------------------------
+// Runs of single-child nodes become chain nodes (flat_index.hpp).  Buckets are independent, so the
+// bucket range is cut into one piece per thread; a counting pass sizes every piece's share of the
+// output, a second pass writes it.
+struct Compressor {
+	const FlatVec<uint32_t>::type &nodes; // decoded: 4 child refs per node
+	uint32_t *out;                        // compressed nodes (NULL: count only)
+	uint64_t next;                        // next free compressed node
+
+	uint32_t run(uint32_t ref) {
+		if (ref == kRefNone || refIsLeaf(ref))
+			return ref;
+		// follow single-child nodes
+		uint64_t bases = 0;
+		uint32_t len = 0, cur = ref;
+		while (cur != kRefNone && !refIsLeaf(cur) && len < kChainMaxBases) {
+			const uint32_t *ch = &nodes[4 * (size_t) refNodeId(cur)];
+			int only = -1, n = 0;
+			for (int c = 0; c < 4; c++)
+				if (ch[c] != kRefNone) {
+					only = c;
+					n++;
+				}
+			if (n != 1)
+				break;
+			bases = (bases << 2) | (uint64_t) only;
+			len++;
+			cur = ch[only];
+		}
+		const uint64_t at = next++;
+		if (len > 0) {
+			const uint32_t follow = run(cur);
+			if (out != NULL) {
+				out[4 * at + 0] = kChainTag | len;
+				out[4 * at + 1] = (uint32_t) (bases >> 32);
+				out[4 * at + 2] = (uint32_t) bases;
+				out[4 * at + 3] = follow;
+			}
+		} else {
+			const uint32_t *ch = &nodes[4 * (size_t) refNodeId(ref)];
+			uint32_t kids[4];
+			for (int c = 0; c < 4; c++)
+				kids[c] = run(ch[c]);
+			if (out != NULL)
+				for (int c = 0; c < 4; c++)
+					out[4 * at + c] = kids[c];
+		}
+		return (uint32_t) at + 1;
+	}
+};
+
+// x.nodes / x.bucket_root -> cnodes + compressed roots (one per bucket, file order)
+int compressTries(const DecodedIndex &x, FlatVec<uint32_t>::type &cnodes, FlatVec<uint32_t>::type &croot, std::string &err) {
+	if (x.numLeaves() > kMaxLeavesPerTable) {
+		err = "Index too large: more than 2^30 leaves in one table.";
+		return CQ_ENOMEM;
+	}
+	const size_t nb = x.bucket_root.size();
+	croot.resize(nb);
+	const unsigned T = flattenThreads();
+	std::vector<uint64_t> need(T + 1, 0);
+	{
+		std::vector<std::thread> pool;
+		for (unsigned p = 0; p < T; p++)
+			pool.emplace_back([&, p]() {
+				Compressor c = {x.nodes, NULL, 0};
+				for (size_t i = nb * p / T; i < nb * (p + 1) / T; i++)
+					c.run(x.bucket_root[i]);
+				need[p + 1] = c.next;
+			});
+		for (auto &th : pool) th.join();
+	}
+	for (unsigned p = 0; p < T; p++)
+		need[p + 1] += need[p];
+	if (need[T] >= 0x7FFFFFFFull) {
+		err = "Index too large: more than 2^31 trie nodes in one table.";
+		return CQ_ENOMEM;
+	}
+	cnodes.resize(4 * (size_t) need[T]);
+	{
+		std::vector<std::thread> pool;
+		for (unsigned p = 0; p < T; p++)
+			pool.emplace_back([&, p]() {
+				Compressor c = {x.nodes, cnodes.data(), need[p]};
+				for (size_t i = nb * p / T; i < nb * (p + 1) / T; i++)
+					croot[i] = c.run(x.bucket_root[i]);
+			});
+		for (auto &th : pool) th.join();
+	}
+	return CQ_OK;
+}
+
 } // namespace
 
 int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatIndex &out, std::string &err) {
@@ -79,6 +171,11 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 	if (load_factor <= 0.0 || load_factor > 1.0)
 		load_factor = 0.30;
 	out.hash_len = u.hash_len;
+	FlatVec<uint32_t>::type croot[2];
+	int rc_c;
+	if ((rc_c = compressTries(u, out.cnodes_u, croot[0], err)) != 0) return rc_c;
+	if ((rc_c = compressTries(d, out.cnodes_d, croot[1], err)) != 0) return rc_c;
+	if (getenv("CAMMIQ_VERBOSE")) fprintf(stderr, "[flatten] tries compressed %.0f ms: %zu -> %zu and %zu -> %zu nodes\n", std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count(), u.nodes.size() / 4, out.cnodes_u.size() / 4, d.nodes.size() / 4, out.cnodes_d.size() / 4);
 	uint64_t upper = u.bucket_key.size() + d.bucket_key.size();
 	uint64_t want = (uint64_t) ((double) upper / (load_factor * kSlotsPerBucket)) + 1;
 	uint64_t nb = 64;
@@ -181,7 +278,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 						}
 						// a repeated key inside one file: the later bucket replaces the earlier one, as
 						// map64[bucket] = root does (hashtrie.cpp:500)
-						hit.b->ref[hit.k][t] = x.bucket_root[e.i];
+						hit.b->ref[hit.k][t] = croot[t][e.i];
 					};
 					uint64_t queued = 0;
 					for (size_t i = 0; i < x.bucket_key.size(); i++) {
@@ -216,7 +313,7 @@ int flattenIndices(DecodedIndex &u, DecodedIndex &d, double load_factor, FlatInd
 			// wraps into buckets of another (finished) range
 			SlotRef s = probeInsert(out.table, mask, shift, u.hash_len, x.bucket_key[df.index], fresh);
 			n_keys += fresh ? 1 : 0;
-			s.b->ref[s.k][df.table] = x.bucket_root[df.index];
+			s.b->ref[s.k][df.table] = croot[df.table][df.index];
 		}
 	}
 	out.n_keys = n_keys;
@@ -240,9 +337,25 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 	words = std::min<uint64_t>(words, max_bytes / 8);
 	words = std::min<uint64_t>(words, (1ull << 31));
 	words &= ~127ull; // whole 1 KB blocks
-	if (words * 64 < fi.n_keys * kFilterMinBitsPerKey)
-		return; // would not fit L2 at a useful false-positive rate: probe the table directly
-	fi.filter.assign(words, 0);
+	fi.filter_sel_mask = kFilterSelAll;
+	fi.filter_sieve = false;
+	if (words * 64 < fi.n_keys * kFilterMinBitsPerKey) {
+		// not selective at this size: use it as a sieve in front of the table probe, with the number
+		// of bits per key that minimises the share of positions passing (about ln 2 * bits per key)
+		if (words * 64 < fi.n_keys)
+			return; // below one bit per key nothing is gained
+		const double bpk = (double) (words * 64) / (double) fi.n_keys;
+		fi.filter_sel_mask = bpk >= 5.0 ? kFilterSelAll : bpk >= 2.5 ? 0x00770077u : 0x00070007u;
+		fi.filter_sieve = true;
+	}
+	// test hook: CAMMIQ_FILTER_FORCE_SIEVE = 1, 2 or 4 selector pairs puts any index in the sieve regime
+	if (const char *force = getenv("CAMMIQ_FILTER_FORCE_SIEVE")) {
+		const int k = atoi(force);
+		fi.filter_sel_mask = k >= 4 ? kFilterSelAll : k >= 2 ? 0x00770077u : 0x00070007u;
+		fi.filter_sieve = true;
+	}
+	// with selector pairs switched off the test looks at bit 0 of the word in their place
+	fi.filter.assign(words, fi.filter_sel_mask == kFilterSelAll ? 0ull : 1ull);
 	fi.filter_words = (uint32_t) words;
 	const unsigned T = flattenThreads();
 	std::vector<std::thread> pool;
@@ -257,7 +370,7 @@ void buildFilter(FlatIndex &fi, uint64_t max_bytes) {
 					uint32_t A, B;
 					const uint64_t key = stored & ~kKeyOccupied, canon = canonicalKeyHost(key, fi.hash_len);
 					filterHash(canon, A, B);
-					__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_words)], filterMask(B), __ATOMIC_RELAXED);
+					__atomic_fetch_or(&fi.filter[filterWordIndex(A, fi.filter_words)], filterMask(B, fi.filter_sel_mask), __ATOMIC_RELAXED);
 				}
 		});
 	for (auto &th : pool) th.join();
@@ -271,7 +384,7 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 		const uint64_t canon = canonicalKeyHost(bucket, fi.hash_len);
 		filterHash(canon, A, B);
 		uint64_t w = fi.filter[filterWordIndex(A, fi.filter_words)];
-		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B))
+		if (!filterTest((uint32_t) w, (uint32_t) (w >> 32), B, fi.filter_sel_mask))
 			return UINT64_MAX;
 	}
 	uint64_t b = homeBucketHost(bucket, fi.hash_len, fi.table_shift);
@@ -289,17 +402,37 @@ uint64_t flatFind(const FlatIndex &fi, int table, uint64_t bucket, const uint8_t
 			break;
 		b = (b + 1) & mask;
 	}
-	const DecodedIndex &x = table == CQ_TABLE_U ? fi.u : fi.d;
+	const FlatVec<uint32_t>::type &cn = table == CQ_TABLE_U ? fi.cnodes_u : fi.cnodes_d;
 	size_t i = 0;
 	while (ref != kRefNone) {
 		if (refIsLeaf(ref))
 			return refLeafId(ref);
-		if (i >= len)
-			return UINT64_MAX;
-		int code = baseCode(cand[i++]);
-		if (code < 0)
-			return UINT64_MAX;
-		ref = x.nodes[4 * (size_t) refNodeId(ref) + code];
+		const uint32_t *nd = &cn[4 * (size_t) refNodeId(ref)];
+		if ((nd[0] & kChainTag) == kChainTag) {
+			// a run of single-child nodes: every base of it must be there and match
+			const uint32_t n = nd[0] & 63u;
+			const uint64_t want = ((uint64_t) nd[1] << 32) | nd[2];
+			if (i + n > len)
+				return UINT64_MAX;
+			uint64_t have = 0;
+			for (uint32_t t = 0; t < n; t++) {
+				int code = baseCode(cand[i + t]);
+				if (code < 0)
+					return UINT64_MAX;
+				have = (have << 2) | (uint64_t) code;
+			}
+			if (have != want)
+				return UINT64_MAX;
+			i += n;
+			ref = nd[3];
+		} else {
+			if (i >= len)
+				return UINT64_MAX;
+			int code = baseCode(cand[i++]);
+			if (code < 0)
+				return UINT64_MAX;
+			ref = nd[code];
+		}
 	}
 	return UINT64_MAX;
 }

@@ -9,8 +9,12 @@
 //                  probe sequence passed this bucket lies further on.  A lookup stops at the first
 //                  bucket that holds the key or whose flag is clear, so a miss costs one sector
 //                  unless a key really spilled past the bucket (2 % of buckets at load 0.30).
-//   trie nodes     per table, 4 child refs (16 bytes) per internal node; only buckets whose
-//                  root is not already a leaf have any (rare when h == k).
+//   trie nodes     per table, 16 bytes per node; only buckets whose root is not already a leaf
+//                  have any (rare when h == k).  A node with several children holds its 4 child
+//                  refs; a run of single-child nodes -- what almost every key longer than h is --
+//                  is ONE chain node {tag | length, up to 32 bases, next ref}: a lookup compares
+//                  the read's next bases with it in one step instead of walking one dependent
+//                  load per base (Hash::find64_p's loop, hashtrie.cpp:356-366, on compressed paths).
 //   leaf refs      per table, the genome id(s) the classification needs: u32 for U,
 //                  {u32,u32} for D.  The remaining leaf fields (ucount, depth) stay on the
 //                  host for the ILP set-up.
@@ -61,6 +65,12 @@ inline uint64_t mixKey(uint64_t x) {
 // The hash runs once per read position and is deliberately lean: two independent multiply-add
 // hashes of the key's 32-bit halves (4 IMAD), the word index from the high bits of the first,
 // the bit selectors from the second.
+// Two regimes.  With at least kFilterMinBitsPerKey bits per key the filter is selective (a few
+// false positives per read) and a position that passes goes straight to the table probe of
+// phase 2.  An index too large for that (cfg4: 3.5e8 keys) still gets a 64 MB filter, used as a
+// SIEVE: fewer bits per key are set (filter_sel_mask switches selectors off) and a position
+// that passes -- about half of them at 1.5 bits per key -- loads its table bucket's keys right
+// in phase 1.  The sieve halves the HBM accesses of the regime that is bound by them.
 static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
 static const uint32_t kFilterMinBitsPerKey = 8;
 
@@ -117,8 +127,13 @@ inline uint32_t filterWordIndex(uint32_t A, uint32_t words) {
 // of B & 0x7777, bits inside those bytes = the four nibbles of (B >> 16) & 0x7777.  On the device
 // that is two byte permutes: one gathers the four selected bytes of the word, one builds the four
 // one-bit masks from a constant table -- no variable shifts.
-inline uint64_t filterMask(uint32_t B) {
+// `sel` = 0x77777777 uses all four pairs; a sieve with fewer bits per key zeroes nibbles of it
+// (0x00770077: two pairs, 0x00070007: one), which turns the unused pairs into (byte 0, bit 0) -- a bit
+// the builder then sets in every word.
+static const uint32_t kFilterSelAll = 0x77777777u;
+inline uint64_t filterMask(uint32_t B, uint32_t sel = kFilterSelAll) {
 	uint64_t m = 0;
+	B &= sel;
 	for (int i = 0; i < 4; i++)
 		m |= 1ull << (8 * ((B >> (4 * i)) & 7u) + ((B >> (16 + 4 * i)) & 7u));
 	return m;
@@ -126,13 +141,13 @@ inline uint64_t filterMask(uint32_t B) {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline bool filterTest(uint32_t x, uint32_t y, uint32_t B) {
+inline bool filterTest(uint32_t x, uint32_t y, uint32_t B, uint32_t sel = kFilterSelAll) {
 #if defined(__CUDA_ARCH__)
-	const uint32_t bytes = __byte_perm(x, y, B & 0x7777u);
-	const uint32_t bits = __byte_perm(0x08040201u, 0x80402010u, (B >> 16) & 0x7777u);
+	const uint32_t bytes = __byte_perm(x, y, B & sel & 0xFFFFu);
+	const uint32_t bits = __byte_perm(0x08040201u, 0x80402010u, (B & sel) >> 16);
 	return (~bytes & bits) == 0u;
 #else
-	const uint64_t m = filterMask(B), w = (uint64_t) x | ((uint64_t) y << 32);
+	const uint64_t m = filterMask(B, sel), w = (uint64_t) x | ((uint64_t) y << 32);
 	return (w & m) == m;
 #endif
 }
@@ -177,6 +192,13 @@ struct RawArray {
 	const T &operator[](size_t i) const { return p[i]; }
 };
 
+// Chain node: word 0 = kChainTag | number of bases (1..32), words 1-2 = the bases (2-bit codes,
+// first base most significant, right-aligned in 64 bits: word 1 = high half), word 3 = the ref
+// that follows the chain.  Leaf refs carry 0x80000000 | id, so the tag needs ids below 2^30.
+static const uint32_t kChainTag = 0xC0000000u;
+static const uint32_t kChainMaxBases = 32;
+static const uint64_t kMaxLeavesPerTable = 1ull << 30;
+
 struct FlatIndex {
 	uint32_t hash_len = 0;
 	uint64_t n_table_buckets = 0; // power of two, 2^6 .. 2^32
@@ -185,7 +207,11 @@ struct FlatIndex {
 	RawArray<TableBucket> table;  // n_table_buckets
 	std::vector<uint64_t> filter; // any multiple of 128 words, empty = no filter (index too large for L2)
 	uint32_t filter_words = 0;    // = filter.size()
+	uint32_t filter_sel_mask = kFilterSelAll; // selector pairs in use (see filterTest)
+	bool filter_sieve = false;    // too few bits per key to be selective: passing positions probe the table in phase 1
 	DecodedIndex u, d;            // leaves (file order) + trie nodes + buckets of each table
+	// path-compressed tries (what the device and flatFind walk); the table refs point into these
+	FlatVec<uint32_t>::type cnodes_u, cnodes_d;
 	double decode_ms = 0, flatten_ms = 0;
 
 	uint64_t deviceBytes() const;

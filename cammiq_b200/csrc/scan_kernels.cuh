@@ -65,7 +65,7 @@ static const int kTileBufs = CAMMIQ_TILE_BUFS; // 2: the next tile's copy overla
 static const int kLightHits = 16;             // longer hit lists are deduplicated by the whole warp
 static const int kProbeUnroll = 4;            // micro-benchmark unroll
 static const int kMaxBlocksPerSM = 4;
-static const uint32_t kMaxSmemGenomes = 8191; // 2*(G+1) u32 block counters must fit 64 KB
+static const uint32_t kMaxSmemGenomes = 1023; // 2*(G+1) u32 block counters stay below 8 KB of shared memory
 static const uint32_t kSetEmpty = 0xFFFFFFFFu;
 
 struct ScanParams {
@@ -75,6 +75,7 @@ struct ScanParams {
 	uint32_t table_shift;     // home bucket of a key = tableBucket(filter hash B of its canonical h-mer, table_shift)
 	const uint2 *filter;      // NULL: no filter, phase 1 probes the table
 	uint32_t filter_words;    // number of 64-bit filter words
+	uint32_t filter_sel;      // selector pairs of the filter test in use (flat_index.hpp, filterTest)
 	const uint32_t *nodes_u, *nodes_d;
 	const uint32_t *leaf_u_ref;
 	const uint2 *leaf_d_ref;
@@ -222,25 +223,58 @@ __device__ __forceinline__ unsigned long long packedWindow(uint32_t pk_addr, uin
 	return (((unsigned long long) hi << 32) | lo) >> (64 - 2 * h);
 }
 
-// Walk the CSR trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).  The forward
-// strand consumes the bases right of the window, the reverse-complement strand the complemented
-// bases left of it; `next` = first base to consume / one past it.
+// the n-base window (n <= 32) starting at base i of a packed read, right-aligned
+__device__ __forceinline__ unsigned long long packedBases(uint32_t pk_addr, uint32_t i, uint32_t n) {
+	const uint32_t a = pk_addr + ((i >> 4) << 2), sh = 2u * (i & 15u);
+	const uint32_t w0 = ldsU32(a), w1 = ldsU32(a + 4), w2 = ldsU32(a + 8);
+	const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+	return (((unsigned long long) hi << 32) | lo) >> (64 - 2 * n);
+}
+
+// Walk the path-compressed trie below a bucket root: find64_p's loop (hashtrie.cpp:356-366).  The
+// forward strand consumes the bases right of the window, the reverse-complement strand the
+// complemented bases left of it; `next` = first base to consume / one
+// past it.  A chain node stands for a run of single-child nodes: all its bases must be there and
+// match (an internal node is never an answer), checked with one comparison.
 template <bool REVERSE>
 __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes, uint32_t pk_addr, uint32_t rl, uint32_t next) {
 	while (ref != kRefNone && !(ref & kRefLeafTag)) {
-		uint32_t code;
-		if (REVERSE) {
-			if (next == 0)
+		uint4 nd;
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+			: "=r"(nd.x), "=r"(nd.y), "=r"(nd.z), "=r"(nd.w) : "l"(nodes + 4 * (size_t) (ref - 1)));
+		if ((nd.x & kChainTag) == kChainTag) {
+			const uint32_t n = nd.x & 63u;
+			const unsigned long long want = ((unsigned long long) nd.y << 32) | nd.z;
+			unsigned long long have;
+			if (REVERSE) {
+				if (next < n)
+					return kRefNone;
+				next -= n;
+				have = revcompKey(packedBases(pk_addr, next, n), n);
+			} else {
+				if (next + n > rl)
+					return kRefNone;
+				have = packedBases(pk_addr, next, n);
+				next += n;
+			}
+			if (have != want)
 				return kRefNone;
-			next--;
-			code = 3u - packedBase(pk_addr, next);
+			ref = nd.w;
 		} else {
-			if (next >= rl)
-				return kRefNone;
-			code = packedBase(pk_addr, next);
-			next++;
+			uint32_t code;
+			if (REVERSE) {
+				if (next == 0)
+					return kRefNone;
+				next--;
+				code = 3u - packedBase(pk_addr, next);
+			} else {
+				if (next >= rl)
+					return kRefNone;
+				code = packedBase(pk_addr, next);
+				next++;
+			}
+			ref = code == 0 ? nd.x : code == 1 ? nd.y : code == 2 ? nd.z : nd.w;
 		}
-		ref = loadStreamU32(&nodes[4 * (size_t) (ref - 1) + code]);
 	}
 	return ref;
 }
@@ -326,7 +360,9 @@ __device__ __forceinline__ void drainQueue(const ScanParams &p, WarpState &ws, u
 	__syncwarp();
 }
 
-template <int MODE, bool FILTER>
+// FILTER: 0 = no filter (phase 1 loads every position's bucket keys), 1 = selective L2 filter,
+// 2 = L2 filter as a sieve in front of the bucket-key loads of phase 1 (index too large to be selective)
+template <int MODE, int FILTER>
 __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_kernel(ScanParams p) {
 	// [8 warps][kTileBufs buffers][32 * words_per_read words: a packed tile] | [2*(G+1) u32 genome counters]
 	extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -464,6 +500,8 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 					ff[t] = make_uint2(0u, 0u);
 					if ((uint32_t) t < count)
 						ff[t] = loadFilterWord(p.filter + filterWordIndex(A, p.filter_words), pol_keep);
+					if (FILTER == 2)
+						kf[t] = hf;
 				} else {
 					kf[t] = hf;
 					bk0[t] = bk1[t] = 0ull;
@@ -475,13 +513,23 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 					}
 				}
 			}
+			if (FILTER == 2) {
+				// sieve: only the positions whose filter word passes (about half at 1.5 bits per key) go
+				// to HBM for their bucket's keys; an all-zero word (past the strip's end) never passes
+#pragma unroll
+				for (int t = 0; t < kStrip; t++) {
+					bk0[t] = bk1[t] = 0ull;
+					if (filterTest(ff[t].x, ff[t].y, bsel[t], p.filter_sel))
+						loadBucketKeys(p.table + tableBucket(bsel[t], p.table_shift), bk0[t], bk1[t]);
+				}
+			}
 #pragma unroll
 			for (int t = 0; t < kStrip; t++) {
 				bool cand_f, cand_r;
-				if (FILTER) {
+				if (FILTER == 1) {
 					// the canonical h-mer of the window may be a key, in either orientation: phase 2 looks
 					// for both.  An all-zero word (position past the strip's end) fails the test.
-					cand_f = cand_r = filterTest(ff[t].x, ff[t].y, bsel[t]);
+					cand_f = cand_r = filterTest(ff[t].x, ff[t].y, bsel[t], p.filter_sel);
 				} else {
 					// candidate = the bucket holds the key, or a key spilled past this bucket; the reverse
 					// strand's key is recomputed rather than kept live across the loads
@@ -497,7 +545,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 					if (strands) {
 						ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) ((slot << 10) | (strands << 8) | (i0 + t));
 						// the candidate's bucket travels from HBM to L2 while the rest of the tile is probed
-						if (FILTER)
+						if (FILTER == 1)
 							prefetchL2(p.table + tableBucket(bsel[t], p.table_shift));
 					}
 					nq += __popc(m);
@@ -739,6 +787,8 @@ struct PackParams {
 	const uint8_t *lengths_in;
 	uint64_t n_reads, n_padded; // n_padded = n_reads rounded up to 32
 	uint32_t words_per_read;
+	uint32_t reads_per_block;  // floor(256 / words_per_read)
+	uint32_t inv_words;        // ceil(2^16 / words_per_read)
 	uint32_t *words;           // [n_padded][words_per_read]
 	uint8_t *lengths_out;      // ASCII input: a copy of lengths_in in which invalid reads are zeroed
 };
@@ -751,11 +801,14 @@ __device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
 
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
-	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	const uint64_t r = idx / q.words_per_read;
-	const uint32_t c = (uint32_t) (idx - r * q.words_per_read);
-	if (r >= q.n_padded)
+	// a block takes floor(256 / words_per_read) whole reads: read and word of a thread come from
+	// 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / words_per_read)
+	const uint32_t k = (threadIdx.x * q.inv_words) >> 16;
+	const uint32_t c = threadIdx.x - k * q.words_per_read;
+	const uint64_t r = (uint64_t) blockIdx.x * q.reads_per_block + k;
+	if (k >= q.reads_per_block || r >= q.n_padded)
 		return;
+	const uint64_t idx = r * q.words_per_read + c;
 	uint32_t word = 0;
 	if (r < q.n_reads) {
 		const int n = (int) q.lengths_in[r] - (int) (16u * c); // bases of this read in word c

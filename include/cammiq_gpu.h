@@ -87,8 +87,10 @@ typedef struct {
 	uint64_t n_buckets_d;
 	uint64_t n_keys;         /* distinct h-mers over both tables = occupied table slots */
 	uint64_t n_table_buckets;/* 32-byte buckets in the merged prefix table (power of two) */
-	uint64_t n_nodes_u;      /* CSR trie nodes below non-leaf bucket roots */
+	uint64_t n_nodes_u;      /* trie nodes of the index file below non-leaf bucket roots */
 	uint64_t n_nodes_d;
+	uint64_t n_cnodes_u;     /* device trie nodes after path compression (runs of single-child */
+	uint64_t n_cnodes_d;     /* nodes become one chain node of up to 32 bases) */
 	uint32_t max_ref_id;     /* largest genome id stored in a leaf */
 	uint64_t filter_bytes;   /* membership filter size, 0 = none */
 	uint64_t device_bytes;   /* bytes cq_index_upload will place on the device */
@@ -361,7 +363,8 @@ typedef struct {
 	uint32_t grid_blocks, blocks_per_sm, dyn_smem_bytes, regs_per_thread;
 	/* host packing of the last cq_query: wall time spent in the packer, threads used (0 = off) */
 	double host_pack_ms;
-	uint32_t host_pack_threads, reserved0;
+	uint32_t host_pack_threads;
+	uint32_t smem_carveout_pct; /* shared-memory carve-out the last scan launch asked for (percent of 228 KB) */
 	uint64_t h2d_bytes;   /* bytes the last cq_query / cq_query_packed copied host->device */
 } cq_timing;
 /* Synchronises the stream, folds the per-step CUDA events into the sums and returns them. */

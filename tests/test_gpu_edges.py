@@ -119,7 +119,7 @@ def test_palindromic_hmers(ctx, tmp_path, h):
 
 
 def test_more_genomes_than_shared_counters(ctx, tmp_path):
-    """G = 9000 > 8191: genome counters fall back to global 64-bit atomics."""
+    """G = 9000 > 1023: genome counters fall back to global 64-bit atomics."""
     rng = np.random.default_rng(7)
     seq = random_seq(rng, 6000)
     G = 9000

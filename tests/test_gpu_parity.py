@@ -72,6 +72,31 @@ def test_gpu_matches_oracle_every_read(ctx, case, mode):
             assert got["pairs"] == want["pairs"]
 
 
+@pytest.mark.parametrize("pairs", [1, 2, 4])
+@pytest.mark.parametrize("case", golden_cases())
+def test_sieve_regime_matches_oracle(ctx, case, pairs, monkeypatch):
+    """The regime of indices too large for a selective filter (BASELINE configs[3]): the L2 filter
+    as a sieve, passing positions load their bucket keys in phase 1.  Forced on the golden indices
+    with 1, 2 and 4 bits per key (CAMMIQ_FILTER_FORCE_SIEVE) and a filter small enough that a good
+    share of the positions pass."""
+    c = load_case(case)
+    oi_u, oi_d = ol.OracleIndex(c["iu"]), ol.OracleIndex(c["id"])
+    monkeypatch.setenv("CAMMIQ_FILTER_FORCE_SIEVE", str(pairs))
+    for mode, m in (("p", ol.MODE_P), ("sc", ol.MODE_SC)):
+        want = ol.oracle_query(oi_u, oi_d, m, c["G"], c["bases"], c["offsets"], c["lengths"], per_read=True, leaf_cap=128)
+        for lf in (0.0, 0.95):
+            idx, got = run_gpu(ctx, c, mode, load_factor=lf, filter_bytes=8192, per_read=True, leaf_cap=128)
+            for k in ("cnt_u", "cnt_d", "read_class", "read_rid_a", "read_rid_b", "read_nleaf_u", "read_nleaf_d",
+                      "read_leaf_u", "read_leaf_d"):
+                assert np.array_equal(got[k], want[k]), (k, lf, mode)
+            assert (int(got["nundet"]), int(got["nconf"])) == (int(want["nundet"]), int(want["nconf"]))
+            if mode == "p":
+                assert np.array_equal(got["rcount_u"], want["rcount_u"]) and np.array_equal(got["rcount_d"], want["rcount_d"])
+            else:
+                assert got["pairs"] == want["pairs"]
+            ctx.reset()
+
+
 def test_counters_accumulate_and_reset(ctx):
     """Device counters live across calls until cq_reset, like the reference's counters until
     resetCounters (query.cpp:259-260, 1820-1840); splitting a file into batches is exact."""

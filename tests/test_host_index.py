@@ -100,13 +100,18 @@ def test_parallel_decode_of_many_buckets_matches_oracle(tmp_path, threads, monke
 
 
 @pytest.mark.parametrize("case", golden_cases())
-@pytest.mark.parametrize("load_factor", [0.0, 0.95])
-def test_flat_lookup_matches_oracle_find(case, load_factor):
-    """Every h-mer window of a read corpus (both strands): flattened table + CSR trie gives
-    the same leaf as the oracle's find64_p (test pyramid item 2)."""
+@pytest.mark.parametrize("load_factor,sieve", [(0.0, None), (0.95, None), (0.95, "1"), (0.0, "2")])
+def test_flat_lookup_matches_oracle_find(case, load_factor, sieve, monkeypatch):
+    """Every h-mer window of a read corpus (both strands): flattened table + path-compressed trie
+    (behind the selective filter, or the 1- / 2-bit sieve of oversized indices) gives the same
+    leaf as the oracle's find64_p (test pyramid item 2)."""
     d = os.path.join(GOLD, case)
     iu, idd = os.path.join(d, "index_u.bin1"), os.path.join(d, "index_d.bin2")
+    if sieve:
+        monkeypatch.setenv("CAMMIQ_FILTER_FORCE_SIEVE", sieve)
     idx = cq.Index(iu, idd, load_factor)
+    if sieve:
+        idx.set_filter_budget(8192)
     ou, od = ol.OracleIndex(iu), ol.OracleIndex(idd)
     h = idx.hash_len
     reads = synth.read_fastq(os.path.join(d, "reads.fq"))[:300]

@@ -9,14 +9,15 @@ python tools/kernel_ab.py > $out/ab_main.json 2> $out/ab_main.err
 echo "main rc=$?"; cat $out/ab_main.json
 timeout 1200 python -m pytest tests -m gpu -x -q > $out/gputests.log 2>&1
 echo "tests rc=$?"; tail -5 $out/gputests.log
-for v in s8b3 s8b4 s8b2 s4b4; do
+for v in none; do
   CAMMIQ_LIB=$PWD/cammiq_b200/variants/libcammiq_gpu_$v.so python tools/kernel_ab.py >> $out/ab_variants.jsonl 2>> $out/ab_variants.err
 done
 cat $out/ab_variants.jsonl
 python tools/kernel_ab.py --packed >> $out/ab_more.jsonl 2>> $out/ab_more.err
 python tools/kernel_ab.py --workload cfg3 >> $out/ab_more.jsonl 2>> $out/ab_more.err
 python tools/kernel_ab.py --filter-mb 0 >> $out/ab_more.jsonl 2>> $out/ab_more.err
-python tools/kernel_ab.py --filter-mb 32 >> $out/ab_more.jsonl 2>> $out/ab_more.err
+python tools/kernel_ab.py --filter-mb 8 >> $out/ab_more.jsonl 2>> $out/ab_more.err
+python tools/kernel_ab.py --filter-mb 16 >> $out/ab_more.jsonl 2>> $out/ab_more.err
 python tools/kernel_ab.py --filter-mb 48 >> $out/ab_more.jsonl 2>> $out/ab_more.err
 python tools/kernel_ab.py --mode sc >> $out/ab_more.jsonl 2>> $out/ab_more.err
 cat $out/ab_more.jsonl
