@@ -71,7 +71,11 @@ inline uint64_t mixKey(uint64_t x) {
 // SIEVE: fewer bits per key are set (filter_sel_mask switches selectors off) and a position
 // that passes -- about half of them at 1.5 bits per key -- loads its table bucket's keys right
 // in phase 1.  The sieve halves the HBM accesses of the regime that is bound by them.
-static const uint64_t kFilterMaxBytesDefault = 64ull << 20;
+// 48 MB, not the 64 MB that a lone gather kernel still finds L2-resident: next to the scan's other
+// traffic a 64 MB filter misses L2 on more than half of its probes (24 GB of DRAM traffic per 10M
+// reads against 15 GB at 40-48 MB, profiles/r02_filter_size_sweep.json); the extra false positives
+// of the smaller filter (11 instead of 15 bits per key at cfg2) cost less than the misses.
+static const uint64_t kFilterMaxBytesDefault = 48ull << 20;
 static const uint32_t kFilterMinBitsPerKey = 8;
 
 // reverse complement of a 2-bit packed h-mer (first base most significant): complement, then

@@ -107,9 +107,11 @@ void cq_index_free(cq_index *idx);
 int cq_index_get_info(const cq_index *idx, cq_index_info *info);
 /*
  * (Re)build the L2-resident membership filter that fronts the prefix table, using at most
- * max_bytes (a power of two is used; 0 removes the filter, so every position probes the
- * table in HBM).  cq_index_load builds it with a 64 MB budget -- what the B200's L2 serves
- * at full random-gather rate -- and drops it when fewer than 8 bits per key would fit.
+ * max_bytes (whole KB; 0 removes the filter, so every position probes the table in HBM).
+ * cq_index_load builds it with a 48 MB budget -- what stays L2-resident next to the scan's
+ * other traffic on a B200.  With fewer than 8 bits per key the filter is no longer selective
+ * and is used as a sieve instead (1 or 2 bits per key; positions that pass load their bucket's
+ * keys in the same phase); below 1 bit per key it is dropped.
  * Takes effect at the next cq_index_upload.
  */
 int cq_index_set_filter_budget(cq_index *idx, uint64_t max_bytes);

@@ -117,3 +117,40 @@ def test_ilp_inputs_on_the_device(case):
         assert np.allclose(got["genome_wcov_" + tag][1:], gsum[1:], rtol=1e-10, atol=0.0)
         assert np.array_equal(got["genome_rcount_" + tag][1:], grc[1:])
     ctx.close()
+
+
+@pytest.mark.parametrize("case", ["cfg1_small", "deep_h12"])
+def test_ilp_inputs_against_the_reference_expressions(case, tmp_path):
+    """`ref_harness ilp` evaluates the expressions of query.cpp:1087, 1157-1160, 1171-1175 on the
+    reference's own nodes after the reference's own scan (the solver code around them is compiled out
+    without CPLEX / Gurobi).  Per map_sp entry: rcount must be equal, wcov within 1e-12 relative."""
+    import os
+    import subprocess
+    harness = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_harness")
+    if not os.access(harness, os.X_OK):
+        pytest.skip("oracle/_ref not built")
+    c = load_case(case)
+    out = str(tmp_path / "ilp.txt")
+    subprocess.run([harness, "ilp", c["iu"], c["id"], c["map"], "0.01", out, c["fq"]], check=True, capture_output=True)
+    rows = [l.split() for l in open(out)]
+    rl = int(rows[0][1])
+    idx = cq.Index(c["iu"], c["id"])
+    ctx = cq.Context(0).upload(idx, c["G"])
+    res = ctx.query(cq.MODE_P, c["bases"], c["offsets"], c["lengths"])
+    got = ctx.ilp_inputs(float(np.float32(0.01)), rl)
+    n = 0
+    for tag, table, w1, w2, rc in (("U", cq.TABLE_U, got["wcov_u"], None, res["rcount_u"]),
+                                   ("D", cq.TABLE_D, got["wcov_d1"], got["wcov_d2"], res["rcount_d"])):
+        off, ids = idx.map_sp(table, c["G"])
+        for r in rows[1:]:
+            if r[0] != tag:
+                continue
+            g, k = int(r[1]), int(r[2])
+            leaf = int(ids[int(off[g]) + k])
+            assert int(rc[leaf]) == int(r[3])
+            assert abs(w1[leaf] - float(r[4])) <= 1e-12 * max(abs(float(r[4])), 1e-300)
+            if w2 is not None:
+                assert abs(w2[leaf] - float(r[5])) <= 1e-12 * max(abs(float(r[5])), 1e-300)
+            n += 1
+    assert n == len(rows) - 1 and n > 100
+    ctx.close()
