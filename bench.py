@@ -64,6 +64,12 @@ WORKLOADS = {
                       erate=0.07, n_rate=0.01, k=20, lmax=50, seed=6, permille_deep=1000, permille_private=60,
                       permille_pair=800, sample_reads=50_000,
                       desc="adversarial, h=20 < every key length (21..50): each hit walks the trie; 250bp, 7% subs, 1% N"),
+    # hit-uniqueness stress: a dense index (600 keys per kbp block) and nearly error-free 250-bp reads:
+    # about a hundred leaf hits per read, many of them the same leaf on both strands' positions
+    "cfg5_dense": dict(n_genomes=64, genome_len=1_000_000, cluster_size=2, reads=500_000, read_len=250,
+                       erate=0.005, k=26, lmax=50, seed=7, permille_deep=300, permille_private=150,
+                       permille_pair=800, u_per_block=600, d_per_block=600, sample_reads=20_000,
+                       desc="adversarial, hit lists: 64 near-duplicate strains, 600 keys per 1024-base block, 250bp reads, 0.5% subs"),
 }
 STRONG_CFG3_READS = 50_000_000
 
@@ -480,7 +486,7 @@ def oracle_sample_check(cq, ctx, idx_dir, G, reads, lengths, rl, m, mode_pair):
             "ok": all(v.endswith("ok") for v in verdict)}
 
 
-def block_synthetic(cq, name, workdir, steps, warmup, budget_left, modes=("p",), with_harness=True):
+def block_synthetic(cq, name, workdir, steps, warmup, budget_left, modes=("p",), with_harness=True, dedup_ab=False):
     """A secondary shape on the synthetic index writer: throughput of the resident scan, the
     size-independent properties on all reads, per-read parity with the oracle and full-vector parity
     with the reference harness on a sample."""
@@ -514,17 +520,40 @@ def block_synthetic(cq, name, workdir, steps, warmup, budget_left, modes=("p",),
             out["chained_bucket_loads"] = tm["chained_loads"]
             out["launch"] = {"grid": tm["grid_blocks"], "blocks_per_sm": tm["blocks_per_sm"], "dyn_smem": tm["dyn_smem_bytes"],
                              "regs": tm["regs_per_thread"]}
-            if info.filter_bytes == 0:
-                # every read position costs one table sector in HBM: the random-access roofline
+            positions = tm["probes"] / 2
+            sec = t["scan_ms"] * 1e-3
+            if info.filter_bytes == 0 or tm["sieve_loads"] > 0:
+                # the regime bound by random HBM accesses: one table sector per read position, or --
+                # behind the sieve -- per position that passes it
                 gsec = ctx.bench_random_sectors(1 << 28, iters=2)
-                positions = tm["probes"] / 2
+                first = tm["sieve_loads"] if tm["sieve_loads"] > 0 else positions
+                sectors = first + tm["chained_loads"] + tm["bucket_hits"] + tm["leaf_hits"]
                 out["roofline"] = {"bound": "hbm-random", "unit": "G sectors/s", "peak": gsec,
                                    "peak_source": "cq_bench_random_sectors over this table, same run",
-                                   "achieved": positions / (t["scan_ms"] * 1e-3) / 1e9,
-                                   "frac": positions / (t["scan_ms"] * 1e-3) / 1e9 / gsec,
-                                   "achieved_with_chained_loads": (positions + tm["chained_loads"]) / (t["scan_ms"] * 1e-3) / 1e9,
-                                   "note": "achieved = read positions (one 16-byte key load each, one 32-byte sector of HBM) per "
-                                           "second of scan kernel time; chained = further buckets behind an overflow flag"}
+                                   "achieved": sectors / sec / 1e9, "frac": sectors / sec / 1e9 / gsec,
+                                   "read_positions_g_per_s": positions / sec / 1e9,
+                                   "sieve_pass_rate": (tm["sieve_loads"] / positions) if tm["sieve_loads"] > 0 else None,
+                                   "sectors": {"phase1_bucket_keys": first, "chained_buckets": tm["chained_loads"],
+                                               "phase2_buckets": tm["bucket_hits"], "leaf_records": tm["leaf_hits"]},
+                                   "note": "achieved = random 32-byte sectors the scan requests from HBM (bucket keys of phase 1, "
+                                           "chained buckets, phase-2 buckets, leaf records; rcount updates not counted) per second "
+                                           "of scan kernel time, against the measured random-sector rate of this table"}
+                if tm["sieve_loads"] > 0:
+                    g = gather_peak(ctx, info.filter_bytes, carveout_pct=tm["smem_carveout_pct"],
+                                    smem_per_block=tm["smem_carveout_pct"] * 228 * 1024 // 100 // max(tm["blocks_per_sm"], 1) - 1024,
+                                    blocks_per_sm=tm["blocks_per_sm"])
+                    out["roofline"]["l2_gather"] = {"sieve_loads_g_per_s": positions / sec / 1e9, "peak_g_per_s": g,
+                                                    "frac": positions / sec / 1e9 / g}
+    if dedup_ab:
+        # the same scan with every hit list deduplicated by its own lane (the quadratic loop that
+        # was the only path before the warp-cooperative hash set existed)
+        os.environ["CAMMIQ_LIGHT_HITS"] = "100000"
+        try:
+            tq = timed_scan(ctx, cq.MODE_P, steps, warmup)
+        finally:
+            os.environ.pop("CAMMIQ_LIGHT_HITS", None)
+        out["dedup"] = {"warp_cooperative_hash_set_scan_ms": out["scan_ms"], "per_lane_quadratic_scan_ms": tq["scan_ms"],
+                        "speedup": tq["scan_ms"] / out["scan_ms"]}
     # size-independent properties on ALL reads: class counts add up, strand symmetry of the totals
     ctx.reset()
     a = ctx.query(cq.MODE_P, reads.reshape(-1), None, lengths, stride=rl, per_read=True)
@@ -988,6 +1017,8 @@ def run(json_fd):
             blocks = [("cfg1_refbuilt", lambda: block_cfg1_refbuilt(cq, args.steps, args.warmup)),
                       ("cfg5", lambda: block_synthetic(cq, "cfg5", args.workdir, args.steps, args.warmup, budget_left, modes=("p", "sc"))),
                       ("cfg5_deep", lambda: block_synthetic(cq, "cfg5_deep", args.workdir, args.steps, args.warmup, budget_left)),
+                      ("cfg5_dense", lambda: block_synthetic(cq, "cfg5_dense", args.workdir, args.steps, args.warmup, budget_left,
+                                                             dedup_ab=True)),
                       ("cfg4", lambda: block_synthetic(cq, "cfg4", args.workdir, max(2, args.steps // 4), 3, budget_left,
                                                        with_harness=False))]
             for bname, fn in blocks:

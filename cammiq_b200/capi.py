@@ -83,7 +83,7 @@ class Timing(C.Structure):
                 ("steps", C.c_uint64), ("grid_blocks", C.c_uint32), ("blocks_per_sm", C.c_uint32),
                 ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32),
                 ("host_pack_ms", C.c_double), ("host_pack_threads", C.c_uint32), ("smem_carveout_pct", C.c_uint32),
-                ("h2d_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("sieve_loads", C.c_uint64)]
 
 
 class MultiInfo(C.Structure):

@@ -370,7 +370,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaMalloc((void **) &c->d_counts, (ncnt + 4) * sizeof(unsigned long long)));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u, std::max<size_t>(c->n_leaves_u, 1) * 4));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d, std::max<size_t>(c->n_leaves_d, 1) * 4));
-	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 4 * sizeof(unsigned long long)));
+	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 8 * sizeof(unsigned long long)));
 
 	if (!f.filter.empty()) {
 		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), up)) != 0) return rc;
@@ -401,7 +401,26 @@ extern "C" int cq_reset(cq_ctx *c) {
 	CQ_CUDA(cudaMemsetAsync(c->d_counts, 0, (ncnt + 4) * sizeof(unsigned long long), c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_u, 0, std::max<size_t>(c->n_leaves_u, 1) * 4, c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_d, 0, std::max<size_t>(c->n_leaves_d, 1) * 4, c->stream));
+	c->sc_reads_since_reset = 0;
 	return CQ_OK; // stream-ordered; every reader of the counters is on the same stream
+}
+
+// a stage buffer of the chunk pipeline may still be read by the scan that used it kStages chunks
+// ago: a buffer that has to grow waits for that scan first (and grows with headroom, so that
+// chunks of slightly different extents do not reallocate at all)
+template <typename T>
+static int ensureStage(cq_ctx *c, int b, T **ptr, size_t *cap, size_t need) {
+	if (need <= *cap && *ptr != NULL)
+		return CQ_OK;
+	if (*ptr != NULL)
+		CQ_CUDA(cudaEventSynchronize(c->ev_free[b]));
+	if (*ptr) cudaFree(*ptr);
+	*ptr = NULL;
+	*cap = 0;
+	const size_t n = std::max<size_t>(need + need / 8, 1);
+	CQ_CUDA(cudaMalloc((void **) ptr, n * sizeof(T)));
+	*cap = n;
+	return CQ_OK;
 }
 
 template <typename T>
@@ -575,6 +594,8 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	// hit slots spills to global scratch, sized (and grown) for the longest read seen so far
 	const uint32_t max_hits = longest >= c->h ? 4 * (longest - c->h + 1) : 0;
 	sp.spill_stride = max_hits > (uint32_t) kHitSeg ? ((max_hits - kHitSeg + 3) & ~3u) : 4;
+	// CAMMIQ_LIGHT_HITS (experiments): a huge value sends every hit list through the per-lane quadratic path
+	sp.light_hits = getenv("CAMMIQ_LIGHT_HITS") ? (uint32_t) atol(getenv("CAMMIQ_LIGHT_HITS")) : (uint32_t) kLightHits;
 	sp.dedup_slots = 64;
 	while (sp.dedup_slots < 2 * (kHitSeg + sp.spill_stride))
 		sp.dedup_slots <<= 1;
@@ -668,13 +689,15 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 static int prepareOutputs(cq_ctx *c, int mode, uint64_t n) {
 	int rc;
 	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
+	(void) ncnt;
 	if (mode == CQ_MODE_SC) {
-		// worst case every read adds a pair record on top of those already held
-		unsigned long long have = 0;
-		CQ_CUDA(cudaMemcpyAsync(&have, c->d_counts + ncnt + 3, 8, cudaMemcpyDeviceToHost, c->stream));
-		CQ_CUDA(cudaStreamSynchronize(c->stream));
-		size_t need = (size_t) have + n;
+		// worst case every read adds a pair record on top of those already held; the number held is
+		// bounded by the reads submitted since the last reset (no round trip to the device)
+		const size_t have = (size_t) c->sc_reads_since_reset;
+		size_t need = have + n;
+		c->sc_reads_since_reset += n;
 		if (need > c->cap_pairs) {
+			need += need / 4;
 			unsigned long long *np = NULL;
 			CQ_CUDA(cudaMalloc((void **) &np, std::max<size_t>(need, 1) * 8));
 			if (have > 0)
@@ -714,7 +737,7 @@ static int beginStep(cq_ctx *c, cudaEvent_t **sev) {
 		}
 	}
 	*sev = c->steps[c->steps_used++].e;
-	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 32, c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 64, c->stream));
 	return CQ_OK;
 }
 
@@ -865,56 +888,65 @@ static int ensureHost(T **ptr, size_t *cap, size_t need) {
 	return CQ_OK;
 }
 
+// One chunk of reads, as the caller holds them, copied host -> device on the copy stream into
+// stage b and scanned on the compute stream.  `packed`: the caller's buffer holds 2-bit reads.
+static int submitChunkDirect(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
+		const uint8_t *lengths, uint64_t first, uint64_t n, uint64_t k, int b) {
+	int rc;
+	uint64_t lo = ~0ull, hi = 0;
+	uint32_t max_len = 1;
+	if (offsets) {
+		for (uint64_t i = first; i < first + n; i++) {
+			lo = std::min(lo, offsets[i]);
+			hi = std::max(hi, offsets[i] + (packed ? packedBytes(lengths[i]) : lengths[i]));
+			max_len = std::max<uint32_t>(max_len, lengths[i]);
+		}
+	} else {
+		for (uint64_t i = first; i < first + n; i++)
+			max_len = std::max<uint32_t>(max_len, lengths[i]);
+		// fixed stride: only the reads within 255 bytes of the chunk's end can set its extent
+		lo = first * stride;
+		hi = lo;
+		for (uint64_t i = first + n; i-- > first;) {
+			hi = std::max(hi, i * stride + (packed ? packedBytes(lengths[i]) : lengths[i]));
+			if ((first + n - 1 - i) * stride >= 255)
+				break;
+		}
+	}
+	if (hi < lo) hi = lo;
+	const uint64_t copy_lo = lo & ~15ull, copy_bytes = hi - copy_lo;
+	if ((rc = ensureStage(c, b, &c->d_cbases[b], &c->cap_cbases[b], copy_bytes + 64)) != 0) return rc;
+	if ((rc = ensureStage(c, b, &c->d_clengths[b], &c->cap_clengths[b], n)) != 0) return rc;
+	if (offsets && (rc = ensureStage(c, b, &c->d_coffsets[b], &c->cap_coffsets[b], n)) != 0) return rc;
+	if (k >= (uint64_t) cq_ctx::kStages)
+		CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+	else if (k == 0)
+		CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0)); // after earlier work on the compute stream
+	if (copy_bytes > 0)
+		CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], bases + copy_lo, copy_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+	CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], lengths + first, n, cudaMemcpyHostToDevice, c->copy_stream));
+	if (offsets)
+		CQ_CUDA(cudaMemcpyAsync(c->d_coffsets[b], offsets + first, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+	c->timing.h2d_bytes += copy_bytes + n + (offsets ? n * 8 : 0);
+	CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+	CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+	ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len,
+		packed, NULL, b};
+	if ((rc = launchPack(c, rb)) != 0) return rc;
+	if ((rc = launchScan(c, mode, rb)) != 0) return rc;
+	CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
+	return CQ_OK;
+}
+
 // Chunks of reads flow host -> device on the copy stream while earlier chunks are scanned on
-// the compute stream.  `packed`: the caller's buffer already holds 2-bit reads.
+// the compute stream.
 static int pipelineDirect(cq_ctx *c, int mode, bool packed, const uint8_t *bases, const uint64_t *offsets, uint64_t stride,
 		const uint8_t *lengths, uint64_t n_reads) {
 	int rc;
 	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
-		const int b = (int) (k % cq_ctx::kStages);
 		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
-		uint64_t lo = ~0ull, hi = 0;
-		uint32_t max_len = 1;
-		if (offsets) {
-			for (uint64_t i = first; i < first + n; i++) {
-				lo = std::min(lo, offsets[i]);
-				hi = std::max(hi, offsets[i] + (packed ? packedBytes(lengths[i]) : lengths[i]));
-				max_len = std::max<uint32_t>(max_len, lengths[i]);
-			}
-		} else {
-			for (uint64_t i = first; i < first + n; i++)
-				max_len = std::max<uint32_t>(max_len, lengths[i]);
-			// fixed stride: only the reads within 255 bytes of the chunk's end can set its extent
-			lo = first * stride;
-			hi = lo;
-			for (uint64_t i = first + n; i-- > first;) {
-				hi = std::max(hi, i * stride + (packed ? packedBytes(lengths[i]) : lengths[i]));
-				if ((first + n - 1 - i) * stride >= 255)
-					break;
-			}
-		}
-		if (hi < lo) hi = lo;
-		const uint64_t copy_lo = lo & ~15ull, copy_bytes = hi - copy_lo;
-		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], copy_bytes + 64)) != 0) return rc;
-		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], n)) != 0) return rc;
-		if (offsets && (rc = ensure(&c->d_coffsets[b], &c->cap_coffsets[b], n)) != 0) return rc;
-		if (k >= (uint64_t) cq_ctx::kStages)
-			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
-		else if (k == 0)
-			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[0], 0)); // after earlier work on the compute stream
-		if (copy_bytes > 0)
-			CQ_CUDA(cudaMemcpyAsync(c->d_cbases[b], bases + copy_lo, copy_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-		CQ_CUDA(cudaMemcpyAsync(c->d_clengths[b], lengths + first, n, cudaMemcpyHostToDevice, c->copy_stream));
-		if (offsets)
-			CQ_CUDA(cudaMemcpyAsync(c->d_coffsets[b], offsets + first, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
-		c->timing.h2d_bytes += copy_bytes + n + (offsets ? n * 8 : 0);
-		CQ_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-		CQ_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-		ReadBatch rb = {c->d_cbases[b] - copy_lo, offsets ? c->d_coffsets[b] : NULL, stride, c->d_clengths[b], n, first, max_len,
-			packed, NULL, b};
-		if ((rc = launchPack(c, rb)) != 0) return rc;
-		if ((rc = launchScan(c, mode, rb)) != 0) return rc;
-		CQ_CUDA(cudaEventRecord(c->ev_free[b], c->stream));
+		if ((rc = submitChunkDirect(c, mode, packed, bases, offsets, stride, lengths, first, n, k, (int) (k % cq_ctx::kStages))) != 0)
+			return rc;
 	}
 	return CQ_OK;
 }
@@ -931,9 +963,25 @@ static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uin
 	const AsciiReads in = {bases, offsets, stride, lengths};
 	const bool dense = offsets != NULL;
 	double pack_ms = 0;
+	// The packer is bound by the host's memory bandwidth, the ASCII path by PCIe: with a page-locked
+	// caller buffer every `direct_every`-th chunk crosses PCIe as it is (the copy engine moves it while
+	// the workers pack the next chunks), which shortens the step by the share the two resources allow
+	// (1 chunk in 8 on the hosts measured: 1.0 GB at ~47 GB/s against 1.0 GB packed in ~8.4 ms).
+	int direct_every = getenv("CAMMIQ_DIRECT_EVERY") ? atoi(getenv("CAMMIQ_DIRECT_EVERY")) : 8;
+	if (direct_every > 0) {
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, bases) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+			cudaGetLastError();
+			direct_every = 0; // pageable memory: an "asynchronous" copy of it would block this thread
+		}
+	}
 	for (uint64_t first = 0, k = 0; first < n_reads; first += kChunkReads, k++) {
 		const int b = (int) (k % cq_ctx::kStages);
 		const uint64_t n = std::min<uint64_t>(kChunkReads, n_reads - first);
+		if (direct_every > 0 && k % (uint64_t) direct_every == (uint64_t) direct_every - 1) {
+			if ((rc = submitChunkDirect(c, mode, false, bases, offsets, stride, lengths, first, n, k, b)) != 0) return rc;
+			continue;
+		}
 		// the pinned staging of this slot is free once its previous copy has left the host
 		if (k >= (uint64_t) cq_ctx::kStages)
 			CQ_CUDA(cudaEventSynchronize(c->ev_copied[b]));
@@ -944,9 +992,9 @@ static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uin
 		if (dense && (rc = ensureHost(&c->h_poffsets[b], &c->cap_h_poffsets[b], (size_t) n)) != 0) return rc;
 		packBatch(*c->pool, in, first, n, layout, c->h_pbases[b], c->h_poffsets[b], c->h_plengths[b]);
 		pack_ms += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - p0).count();
-		if ((rc = ensure(&c->d_cbases[b], &c->cap_cbases[b], (size_t) layout.total_bytes + 64)) != 0) return rc;
-		if ((rc = ensure(&c->d_clengths[b], &c->cap_clengths[b], (size_t) n)) != 0) return rc;
-		if (dense && (rc = ensure(&c->d_coffsets32[b], &c->cap_coffsets32[b], (size_t) n)) != 0) return rc;
+		if ((rc = ensureStage(c, b, &c->d_cbases[b], &c->cap_cbases[b], (size_t) layout.total_bytes + 64)) != 0) return rc;
+		if ((rc = ensureStage(c, b, &c->d_clengths[b], &c->cap_clengths[b], (size_t) n)) != 0) return rc;
+		if (dense && (rc = ensureStage(c, b, &c->d_coffsets32[b], &c->cap_coffsets32[b], (size_t) n)) != 0) return rc;
 		if (k >= (uint64_t) cq_ctx::kStages)
 			CQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
 		else if (k == 0)
@@ -1195,8 +1243,9 @@ extern "C" int cq_get_timing(cq_ctx *c, cq_timing *out) {
 	int rc = foldStepEvents(c);
 	if (rc != 0) return rc;
 	if (c->d_probe_count) {
-		unsigned long long pc[4] = {0, 0, 0, 0};
-		CQ_CUDA(cudaMemcpy(pc, c->d_probe_count, 32, cudaMemcpyDeviceToHost));
+		unsigned long long pc[5] = {0, 0, 0, 0, 0};
+		CQ_CUDA(cudaMemcpy(pc, c->d_probe_count, 40, cudaMemcpyDeviceToHost));
+		c->timing.sieve_loads = pc[4];
 		c->timing.probes = pc[0];
 		c->timing.bucket_hits = pc[1];
 		c->timing.leaf_hits = pc[2];

@@ -104,6 +104,7 @@ struct cq_ctx {
 	// SC pair records (device, grows)
 	unsigned long long *d_pairs = NULL;
 	size_t cap_pairs = 0;
+	uint64_t sc_reads_since_reset = 0; // upper bound of the pair records held
 	PairSlot *d_pair_table = NULL, *d_pair_out = NULL; // aggregation scratch of cq_fetch
 	size_t cap_pair_table = 0, cap_pair_out = 0;
 	// per-read outputs (device, sized per call)

@@ -98,7 +98,8 @@ struct ScanParams {
 	uint32_t spill_stride;    // per-read overflow capacity: 4*(longest - h + 1) - kHitSeg hits at most
 	uint32_t *dedup_sets;     // [total warps][dedup_slots] hash-set scratch of the cooperative dedup
 	uint32_t dedup_slots;     // power of two >= 2 * (kHitSeg + spill_stride)
-	unsigned long long *probe_count; // [4]: probes, candidates, leaf hits, chained bucket loads
+	uint32_t light_hits;      // hit lists up to this length are deduplicated by their lane (kLightHits)
+	unsigned long long *probe_count; // [5]: probes, candidates, leaf hits, chained bucket loads, bucket-key loads behind the sieve
 	// optional per-read outputs
 	uint8_t *read_class;
 	uint32_t *read_rid_a, *read_rid_b;
@@ -294,10 +295,14 @@ __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws
 		// what phase 3 will touch for this leaf -- its genome ids and (mode P) its read counter --
 		// is requested now, so that phase 3 finds it in L2
 		const uint32_t lid = leaf[t] & ~kRefLeafTag;
+#ifndef CAMMIQ_NO_LEAF_PREFETCH
 		if (t) prefetchL2(&p.leaf_d_ref[lid]);
 		else prefetchL2(&p.leaf_u_ref[lid]);
+#endif
+#ifndef CAMMIQ_NO_RCOUNT_PREFETCH
 		if (MODE == CQ_MODE_P)
 			prefetchL2(t ? &p.rcount_d[lid] : &p.rcount_u[lid]);
+#endif
 		uint32_t e = (leaf[t] & ~kRefLeafTag) | (t ? kRefLeafTag : 0u);
 		// 16-bit shared counter bumped through its containing 32-bit word
 		uint32_t *word = reinterpret_cast<uint32_t *>(&ws.hit_cnt[slot & ~1u]);
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 	uint32_t *warp_spill = p.hit_spill + warp_global * 32 * p.spill_stride;
 	uint32_t *warp_set = p.dedup_sets + warp_global * p.dedup_slots;
 	uint32_t n_undet = 0, n_conf = 0, n_invalid = 0, n_probes = 0; // per lane (a lane sees < 2^32 / 512 reads per launch)
-	uint32_t n_cand = 0, n_leaf_hits = 0, n_chained = 0; // n_cand warp-uniform, the others per lane
+	uint32_t n_cand = 0, n_leaf_hits = 0, n_chained = 0, n_sieve = 0; // n_cand warp-uniform, the others per lane
 	uint32_t parity = 0; // bit b: phase of buffer b's mbarrier
 
 	const uint32_t n_sub = (uint32_t) ((p.n_reads + 31) / 32); // the host keeps a launch below 2^32 tiles
@@ -519,10 +524,22 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 #pragma unroll
 				for (int t = 0; t < kStrip; t++) {
 					bk0[t] = bk1[t] = 0ull;
-					if (filterTest(ff[t].x, ff[t].y, bsel[t], p.filter_sel))
+					if (filterTest(ff[t].x, ff[t].y, bsel[t], p.filter_sel)) {
 						loadBucketKeys(p.table + tableBucket(bsel[t], p.table_shift), bk0[t], bk1[t]);
+						n_sieve++;
+					}
 				}
 			}
+#ifdef CAMMIQ_INTERLEAVE
+			// the candidates of the PREVIOUS round are resolved while this round's probes are in
+			// flight: their buckets were requested a full round ago, and the filter words of this
+			// round get the time of a phase-2 pass to arrive
+			if (FILTER == 1 && nq > 0) {
+				n_cand += nq;
+				drainQueue<MODE>(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+				nq = 0;
+			}
+#endif
 #pragma unroll
 			for (int t = 0; t < kStrip; t++) {
 				bool cand_f, cand_r;
@@ -545,8 +562,10 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 					if (strands) {
 						ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) ((slot << 10) | (strands << 8) | (i0 + t));
 						// the candidate's bucket travels from HBM to L2 while the rest of the tile is probed
+#ifndef CAMMIQ_NO_BUCKET_PREFETCH
 						if (FILTER == 1)
 							prefetchL2(p.table + tableBucket(bsel[t], p.table_shift));
+#endif
 					}
 					nq += __popc(m);
 				}
@@ -623,7 +642,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 		const bool accepted = cls >= CQ_CLASS_U;
 		const bool want_sets = p.read_nleaf_u != NULL;
 		const bool count_leaves = nh > 0 && ((MODE == CQ_MODE_P && accepted) || want_sets);
-		if (count_leaves && nh <= (uint32_t) kLightHits) {
+		if (count_leaves && nh <= p.light_hits) {
 			for (uint32_t i = 0; i < nh; i++) {
 				uint32_t e = i < (uint32_t) kHitSeg ? ws.hits[lane][i] : my_spill[i - kHitSeg];
 				bool first = true;
@@ -646,7 +665,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 		}
 		// long hit lists (near-duplicate strains, dense indices): the whole warp deduplicates one
 		// read at a time through a hash set in global scratch -- linear instead of quadratic work
-		uint32_t heavy = __ballot_sync(0xffffffffu, count_leaves && nh > (uint32_t) kLightHits);
+		uint32_t heavy = __ballot_sync(0xffffffffu, count_leaves && nh > p.light_hits);
 		while (heavy) {
 			const int src = __ffs(heavy) - 1;
 			heavy &= heavy - 1;
@@ -742,7 +761,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 
 	// ---- block totals ---------------------------------------------------------------------------------
 	unsigned long long undet64 = n_undet, conf64 = n_conf, invalid64 = n_invalid, probes64 = n_probes, leaf64 = n_leaf_hits,
-		chain64 = n_chained;
+		chain64 = n_chained, sieve64 = n_sieve;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
 		undet64 += __shfl_xor_sync(0xffffffffu, undet64, o);
@@ -751,6 +770,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 		probes64 += __shfl_xor_sync(0xffffffffu, probes64, o);
 		leaf64 += __shfl_xor_sync(0xffffffffu, leaf64, o);
 		chain64 += __shfl_xor_sync(0xffffffffu, chain64, o);
+		sieve64 += __shfl_xor_sync(0xffffffffu, sieve64, o);
 	}
 	if (lane == 0) {
 		if (undet64) atomicAdd(&block_tot[0], undet64);
@@ -760,6 +780,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 		if (n_cand) atomicAdd(&p.probe_count[1], (unsigned long long) n_cand);
 		if (leaf64) atomicAdd(&p.probe_count[2], leaf64);
 		if (chain64) atomicAdd(&p.probe_count[3], chain64);
+		if (sieve64) atomicAdd(&p.probe_count[4], sieve64);
 	}
 	__syncthreads();
 	if (p.smem_counters) {

@@ -368,6 +368,7 @@ typedef struct {
 	uint32_t host_pack_threads;
 	uint32_t smem_carveout_pct; /* shared-memory carve-out the last scan launch asked for (percent of 228 KB) */
 	uint64_t h2d_bytes;   /* bytes the last cq_query / cq_query_packed copied host->device */
+	uint64_t sieve_loads; /* last scan, sieve regime: positions that passed the sieve and loaded their bucket's keys */
 } cq_timing;
 /* Synchronises the stream, folds the per-step CUDA events into the sums and returns them. */
 int cq_get_timing(cq_ctx *ctx, cq_timing *out);

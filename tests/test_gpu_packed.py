@@ -103,3 +103,37 @@ def test_host_packing_moves_a_quarter_of_the_bytes(ctx):
     n, total = len(c["lengths"]), int(c["lengths"].astype(np.int64).sum())
     assert plain >= total + 9 * n
     assert packed <= total // 4 + n + 5 * n + 64   # codes + lengths + 32-bit offsets
+
+
+def test_hybrid_transfer_equals_single_call(ctx, monkeypatch):
+    """cq_query from a page-locked buffer sends every n-th chunk over PCIe as ASCII while the host
+    threads pack the others (CAMMIQ_DIRECT_EVERY): 3.3M reads = 4 chunks through both routes and
+    the rotating stage buffers; the totals must be those of the reads queried once, times their
+    multiplicity, whatever the mix."""
+    import ctypes as C
+    c = load_case("long150_h20")
+    ctx.upload(cq.Index(c["iu"], c["id"]), c["G"])
+    ctx.set_host_packing(0)
+    once = ctx.query(cq.MODE_P, c["bases"], c["offsets"], c["lengths"])
+    ctx.reset()
+    reps = 4700                                               # 700 reads x 4700 = 3.29M reads
+    n1, nb = len(c["lengths"]), len(c["bases"])
+    p = C.c_void_p()
+    cq.capi._check(cq.lib().cq_host_alloc(nb * reps, C.byref(p)))
+    try:
+        bases = np.frombuffer((C.c_char * (nb * reps)).from_address(p.value), dtype=np.uint8)
+        bases[:] = np.tile(c["bases"], reps)
+        lengths = np.tile(c["lengths"], reps)
+        offsets = (np.tile(c["offsets"], reps) + np.repeat(np.arange(reps, dtype=np.uint64) * np.uint64(nb), n1)).astype(np.uint64)
+        for every, threads in (("0", 3), ("2", 3), ("3", 2), ("1", 2)):
+            monkeypatch.setenv("CAMMIQ_DIRECT_EVERY", every)
+            ctx.set_host_packing(threads)
+            got = ctx.query(cq.MODE_P, bases, offsets, lengths)
+            ctx.reset()
+            assert np.array_equal(got["cnt_u"], once["cnt_u"] * reps), every
+            assert np.array_equal(got["cnt_d"], once["cnt_d"] * reps), every
+            assert np.array_equal(got["rcount_u"], once["rcount_u"] * reps) and np.array_equal(got["rcount_d"], once["rcount_d"] * reps)
+            assert (int(got["nundet"]), int(got["nconf"])) == (int(once["nundet"]) * reps, int(once["nconf"]) * reps)
+    finally:
+        ctx.set_host_packing(-1)
+        cq.lib().cq_host_free(p)
