@@ -109,18 +109,6 @@ struct ScanParams {
 
 // ------------------------------------------------------------------------------ helpers
 
-// 32 bytes = one sector = one prefix-table bucket, fetched with a single 256-bit load
-// (LDG.E.256 on sm_100a), read-only path, no L1 allocation (every probe is a fresh sector).
-__device__ __forceinline__ void loadBucket(const TableBucket *b, unsigned long long &k0,
-		unsigned long long &k1, unsigned long long &r0, unsigned long long &r1) {
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-		: "=l"(k0), "=l"(k1), "=l"(r0), "=l"(r1) : "l"(b));
-}
-// the two keys of a bucket alone (first half of the sector): phase 1 without a filter
-__device__ __forceinline__ void loadBucketKeys(const TableBucket *b, unsigned long long &k0, unsigned long long &k1) {
-	asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(b));
-}
-
 // L2 residency is the whole point of the filter: its words are loaded with an evict_last
 // policy while every streaming access of the kernel (table sectors, leaf ids, rcount
 // updates, the read tiles) is issued evict_first, so the 64 MB filter is what the L2 keeps.
@@ -134,6 +122,23 @@ __device__ __forceinline__ unsigned long long policyEvictFirst() {
 	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
 	return p;
 }
+// 32 bytes = one sector = one prefix-table bucket, fetched with a single 256-bit load
+// (LDG.E.256 on sm_100a), read-only path, no L1 allocation (every probe is a fresh sector).
+__device__ __forceinline__ void loadBucket(const TableBucket *b, unsigned long long &k0,
+		unsigned long long &k1, unsigned long long &r0, unsigned long long &r1) {
+#ifdef CAMMIQ_STREAM_HINTS
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+		: "=l"(k0), "=l"(k1), "=l"(r0), "=l"(r1) : "l"(b), "l"(policyEvictFirst()));
+#else
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+		: "=l"(k0), "=l"(k1), "=l"(r0), "=l"(r1) : "l"(b));
+#endif
+}
+// the two keys of a bucket alone (first half of the sector): phase 1 without a filter
+__device__ __forceinline__ void loadBucketKeys(const TableBucket *b, unsigned long long &k0, unsigned long long &k1) {
+	asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(b));
+}
+
 __device__ __forceinline__ uint2 loadFilterWord(const uint2 *f, unsigned long long policy) {
 	uint2 v;
 #ifdef CAMMIQ_FILTER_L1_ALLOC
@@ -145,12 +150,20 @@ __device__ __forceinline__ uint2 loadFilterWord(const uint2 *f, unsigned long lo
 }
 __device__ __forceinline__ uint32_t loadStreamU32(const uint32_t *a) {
 	uint32_t v;
+#ifdef CAMMIQ_STREAM_HINTS
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(policyEvictFirst()));
+#else
 	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(a));
+#endif
 	return v;
 }
 __device__ __forceinline__ uint2 loadStreamU32x2(const uint2 *a) {
 	uint2 v;
+#ifdef CAMMIQ_STREAM_HINTS
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(policyEvictFirst()));
+#else
 	asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
+#endif
 	return v;
 }
 __device__ __forceinline__ void redAddStream(uint32_t *a, unsigned long long policy) {
@@ -241,8 +254,13 @@ template <bool REVERSE>
 __device__ __forceinline__ uint32_t descend(uint32_t ref, const uint32_t *__restrict__ nodes, uint32_t pk_addr, uint32_t rl, uint32_t next) {
 	while (ref != kRefNone && !(ref & kRefLeafTag)) {
 		uint4 nd;
+#ifdef CAMMIQ_STREAM_HINTS
+		asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+			: "=r"(nd.x), "=r"(nd.y), "=r"(nd.z), "=r"(nd.w) : "l"(nodes + 4 * (size_t) (ref - 1)), "l"(policyEvictFirst()));
+#else
 		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
 			: "=r"(nd.x), "=r"(nd.y), "=r"(nd.z), "=r"(nd.w) : "l"(nodes + 4 * (size_t) (ref - 1)));
+#endif
 		if ((nd.x & kChainTag) == kChainTag) {
 			const uint32_t n = nd.x & 63u;
 			const unsigned long long want = ((unsigned long long) nd.y << 32) | nd.z;
@@ -292,14 +310,16 @@ __device__ __forceinline__ void collectLeaves(const ScanParams &p, WarpState &ws
 		if (leaf[t] == kRefNone)
 			continue;
 		n_leaf_hits++;
-		// what phase 3 will touch for this leaf -- its genome ids and (mode P) its read counter --
-		// is requested now, so that phase 3 finds it in L2
+		// (requesting what phase 3 will touch for this leaf -- genome ids, read counter -- from HBM
+		// here, like requesting a candidate's bucket when phase 1 finds it, was measured and cost
+		// more than it saved: 4.47 ms with the three prefetches, 4.05-4.22 ms with any one of them
+		// off; the extra lines push filter words out of L2.  Experiment builds can switch them on.)
 		const uint32_t lid = leaf[t] & ~kRefLeafTag;
-#ifndef CAMMIQ_NO_LEAF_PREFETCH
+#ifdef CAMMIQ_LEAF_PREFETCH
 		if (t) prefetchL2(&p.leaf_d_ref[lid]);
 		else prefetchL2(&p.leaf_u_ref[lid]);
 #endif
-#ifndef CAMMIQ_NO_RCOUNT_PREFETCH
+#ifdef CAMMIQ_RCOUNT_PREFETCH
 		if (MODE == CQ_MODE_P)
 			prefetchL2(t ? &p.rcount_d[lid] : &p.rcount_u[lid]);
 #endif
@@ -458,6 +478,29 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 
 		// ---- phase 1: a strip of kStrip positions per lane, all probes in flight before any test ---
 		uint32_t nq = 0; // queue fill, warp-uniform
+		// a strip's positions are tested half a strip late (the second half in the next round): every
+		// filter word has at least half a strip of hashing between its load and its first use
+		uint2 pend_ff[kStrip / 2];
+		uint32_t pend_bsel[kStrip / 2], pend_item = 0;
+#pragma unroll
+		for (int t = 0; t < kStrip / 2; t++) {
+			pend_ff[t] = make_uint2(0u, 0u); // an all-zero word fails the test: nothing is pending yet
+			pend_bsel[t] = 0;
+		}
+		// one position's filter word -> candidate queue (warp-wide: every lane calls it)
+		auto testAndQueue = [&](uint2 word, uint32_t sel_bits, uint32_t item) {
+			const bool cand = filterTest(word.x, word.y, sel_bits, p.filter_sel);
+			const uint32_t m = __ballot_sync(0xffffffffu, cand);
+			if (m) { // warp-uniform; the queue slot of a lane is its rank among the lanes with a candidate
+				if (cand) {
+					ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) (item | (3u << 8)); // either strand may hold the key
+#ifdef CAMMIQ_BUCKET_PREFETCH
+					prefetchL2(p.table + tableBucket(sel_bits, p.table_shift));
+#endif
+				}
+				nq += __popc(m);
+			}
+		};
 		for (uint32_t k0 = 0; k0 < total_strips; k0 += 32) {
 			const uint32_t k = k0 + lane;
 			const bool live = k < total_strips;
@@ -486,6 +529,52 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 			// the bases that enter the window at the strip's later positions, first one in the top bits
 			const uint32_t enter = 2 * h >= 32 ? __funnelshift_l(lo2, lo, 2 * h - 32) : __funnelshift_l(lo, hi, 2 * h);
 
+#ifndef CAMMIQ_NO_PIPELINE
+			if (FILTER == 1) {
+				uint2 ff[kStrip];
+				uint32_t bsel[kStrip];
+				auto probe = [&](int t) {
+					if (t > 0) {
+						const uint32_t c = (enter >> (32 - 2 * t)) & 3u;
+						hf = ((hf << 2) | c) & kmask;                                     // query.cpp:493-494
+						hr = (hr >> 2) | ((unsigned long long) (3u - c) << top_shift);    // the window's reverse complement
+					}
+					// hr is the reverse complement of the window hf covers: ONE probe with the canonical
+					// h-mer answers both strands
+					uint32_t A;
+					filterHash(hf <= hr ? hf : hr, A, bsel[t]);
+					ff[t] = make_uint2(0u, 0u);
+					if ((uint32_t) t < count)
+						ff[t] = loadFilterWord(p.filter + filterWordIndex(A, p.filter_words), pol_keep);
+				};
+				const uint32_t item = (slot << 10) | i0;
+#pragma unroll
+				for (int t = 0; t < kStrip / 2; t++)
+					probe(t);
+#pragma unroll
+				for (int t = 0; t < kStrip / 2; t++) // the previous round's second half
+					testAndQueue(pend_ff[t], pend_bsel[t], pend_item + t);
+#pragma unroll
+				for (int t = kStrip / 2; t < kStrip; t++)
+					probe(t);
+#pragma unroll
+				for (int t = 0; t < kStrip / 2; t++) // this round's first half
+					testAndQueue(ff[t], bsel[t], item + t);
+#pragma unroll
+				for (int t = 0; t < kStrip / 2; t++) {
+					pend_ff[t] = ff[kStrip / 2 + t];
+					pend_bsel[t] = bsel[kStrip / 2 + t];
+				}
+				pend_item = item + kStrip / 2;
+				// a round adds at most 32 * kStrip entries: drain above half
+				if (nq > (uint32_t) (kQueueCap - 32 * kStrip)) {
+					n_cand += nq;
+					drainQueue<MODE>(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
+					nq = 0;
+				}
+				continue;
+			}
+#endif
 			uint2 ff[kStrip];                     // FILTER: filter words
 			uint32_t bsel[kStrip];
 			unsigned long long kf[kStrip];        // !FILTER: forward key, the two keys of the strands' shared bucket
@@ -561,8 +650,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 				if (m) { // warp-uniform; the queue slot of a lane is its rank among the lanes with a candidate
 					if (strands) {
 						ws.queue[nq + __popc(m & lt_mask)] = (uint16_t) ((slot << 10) | (strands << 8) | (i0 + t));
-						// the candidate's bucket travels from HBM to L2 while the rest of the tile is probed
-#ifndef CAMMIQ_NO_BUCKET_PREFETCH
+#ifdef CAMMIQ_BUCKET_PREFETCH
 						if (FILTER == 1)
 							prefetchL2(p.table + tableBucket(bsel[t], p.table_shift));
 #endif
@@ -577,6 +665,13 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 				nq = 0;
 			}
 		}
+#ifndef CAMMIQ_NO_PIPELINE
+		if (FILTER == 1) {
+#pragma unroll
+			for (int t = 0; t < kStrip / 2; t++) // the last round's second half
+				testAndQueue(pend_ff[t], pend_bsel[t], pend_item + t);
+		}
+#endif
 		n_cand += nq;
 		drainQueue<MODE>(p, ws, pk_warp, warp_spill, lane, nq, n_leaf_hits, n_chained);
 
