@@ -1108,7 +1108,7 @@ def run(json_fd):
                        "filter_mb": info.filter_bytes / (1 << 20),
                        "l2_policy": "inputs larger than L2: %.2f GB prefix table + %.2f GB reads per step" % (
                            info.n_table_buckets * 32 / 1e9, n * rl / 1e9),
-                       "parallelism": "index replicated, reads sharded, 1 grouped NCCL reduce/step" if world > 1 else "1 GPU",
+                       "parallelism": "index replicated, reads sharded, counters combined over NCCL once per step (counter block + one grouped launch for the two rcount arrays)" if world > 1 else "1 GPU",
                        "index_prepare_s": t_index},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "d2h_note": "reduced totals, rank 0 only" if world > 1 else "totals",

@@ -554,7 +554,8 @@ static int launchPack(cq_ctx *c, const ReadBatch &rb) {
 	}
 	q.reads_per_block = 256 / q.words_per_read;
 	q.inv_words = (65536 + q.words_per_read - 1) / q.words_per_read;
-	const unsigned blocks = (unsigned) ((q.n_padded + q.reads_per_block - 1) / q.reads_per_block);
+	q.n_passes = (q.n_padded + q.reads_per_block - 1) / q.reads_per_block;
+	const unsigned blocks = (unsigned) std::min<uint64_t>(q.n_passes, (uint64_t) c->n_sms * 16);
 	if (rb.packed)
 		pack_tiles_kernel<true><<<blocks, 256, 0, c->stream>>>(q);
 	else

@@ -905,6 +905,7 @@ struct PackParams {
 	uint32_t words_per_read;
 	uint32_t reads_per_block;  // floor(256 / words_per_read)
 	uint32_t inv_words;        // ceil(2^16 / words_per_read)
+	uint64_t n_passes;         // ceil(n_padded / reads_per_block)
 	uint32_t *words;           // [n_padded][words_per_read]
 	uint8_t *lengths_out;      // ASCII input: a copy of lengths_in in which invalid reads are zeroed
 };
@@ -917,64 +918,70 @@ __device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
 
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
-	// a block takes floor(256 / words_per_read) whole reads: read and word of a thread come from
-	// 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / words_per_read)
+	// a block pass takes floor(256 / words_per_read) whole reads: read and word of a thread come from
+	// 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / words_per_read);
+	// the grid is persistent (a few blocks per SM striding over the passes): with one short-lived
+	// block per pass the launch of 350 000 blocks was what the kernel waited for
 	const uint32_t k = (threadIdx.x * q.inv_words) >> 16;
 	const uint32_t c = threadIdx.x - k * q.words_per_read;
-	const uint64_t r = (uint64_t) blockIdx.x * q.reads_per_block + k;
-	if (k >= q.reads_per_block || r >= q.n_padded)
+	if (k >= q.reads_per_block)
 		return;
-	const uint64_t idx = r * q.words_per_read + c;
-	uint32_t word = 0;
-	if (r < q.n_reads) {
-		const int n = (int) q.lengths_in[r] - (int) (16u * c); // bases of this read in word c
-		if (n > 0) {
-			unsigned long long off;
-			if (PACKED_IN)
-				off = q.offsets32 ? (unsigned long long) q.offsets32[r] : q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
-			else
-				off = q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
-			if (PACKED_IN) {
-				// four bytes of the host-packed read = this word, big-endian; bytes past the read are masked
-				const uint8_t *a = q.bases + off + 4u * c;
-				const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
-				const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
-				const uint32_t w0 = ldgU32(al), w1 = sh ? ldgU32(al + 4) : 0u; // an aligned word never needs the next one
-				word = __byte_perm(__funnelshift_r(w0, w1, sh), 0u, 0x0123);
-			} else {
-				// sixteen ASCII bytes at any alignment: five aligned words, funnel-shifted
-				const uint8_t *a = q.bases + off + 16u * c;
-				const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
-				const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
-				const uint32_t nw = ((uint32_t) ((uintptr_t) a & 3u) + (uint32_t) min(n, 16) + 3u) >> 2; // aligned words the bases touch
-				uint32_t w[5];
+	for (uint64_t pass = blockIdx.x; pass < q.n_passes; pass += gridDim.x) {
+		const uint64_t r = pass * q.reads_per_block + k;
+		if (r >= q.n_padded)
+			break;
+		const uint64_t idx = r * q.words_per_read + c;
+		uint32_t word = 0;
+		if (r < q.n_reads) {
+			const int n = (int) q.lengths_in[r] - (int) (16u * c); // bases of this read in word c
+			if (n > 0) {
+				unsigned long long off;
+				if (PACKED_IN)
+					off = q.offsets32 ? (unsigned long long) q.offsets32[r] : q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
+				else
+					off = q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
+				if (PACKED_IN) {
+					// four bytes of the host-packed read = this word, big-endian; bytes past the read are masked
+					const uint8_t *a = q.bases + off + 4u * c;
+					const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
+					const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
+					const uint32_t w0 = ldgU32(al), w1 = sh ? ldgU32(al + 4) : 0u; // an aligned word never needs the next one
+					word = __byte_perm(__funnelshift_r(w0, w1, sh), 0u, 0x0123);
+				} else {
+					// sixteen ASCII bytes at any alignment: five aligned words, funnel-shifted
+					const uint8_t *a = q.bases + off + 16u * c;
+					const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
+					const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
+					const uint32_t nw = ((uint32_t) ((uintptr_t) a & 3u) + (uint32_t) min(n, 16) + 3u) >> 2; // aligned words the bases touch
+					uint32_t w[5];
 #pragma unroll
-				for (int t = 0; t < 5; t++)
-					w[t] = (uint32_t) t < nw ? ldgU32(al + 4 * t) : 0u;
-				uint32_t bad = 0;
+					for (int t = 0; t < 5; t++)
+						w[t] = (uint32_t) t < nw ? ldgU32(al + 4 * t) : 0u;
+					uint32_t bad = 0;
 #pragma unroll
-				for (int t = 0; t < 4; t++) {
-					const uint32_t d = __funnelshift_r(w[t], w[t + 1], sh);
-					// codes A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
-					// letter each code stands for (one byte permute)
-					const uint32_t t4 = (d >> 1) & 0x03030303u;
-					const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-					const uint32_t nib = code4 | (code4 >> 4);
-					const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-					const int left = n - 4 * t;
-					const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
-					bad |= ((d & 0xDFDFDFDFu) ^ expect4) & live;
-					// four 2-bit codes -> one byte, first base in the top bits
-					word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
+					for (int t = 0; t < 4; t++) {
+						const uint32_t d = __funnelshift_r(w[t], w[t + 1], sh);
+						// codes A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
+						// letter each code stands for (one byte permute)
+						const uint32_t t4 = (d >> 1) & 0x03030303u;
+						const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
+						const uint32_t nib = code4 | (code4 >> 4);
+						const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
+						const int left = n - 4 * t;
+						const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
+						bad |= ((d & 0xDFDFDFDFu) ^ expect4) & live;
+						// four 2-bit codes -> one byte, first base in the top bits
+						word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
+					}
+					if (bad)
+						q.lengths_out[r] = 0; // every thread of an invalid read that sees a bad byte stores the same 0
 				}
-				if (bad)
-					q.lengths_out[r] = 0; // every thread of an invalid read that sees a bad byte stores the same 0
+				if (n < 16)
+					word &= 0xFFFFFFFFu << (32 - 2 * n);
 			}
-			if (n < 16)
-				word &= 0xFFFFFFFFu << (32 - 2 * n);
 		}
+		q.words[idx] = word;
 	}
-	q.words[idx] = word;
 }
 
 // counts[i] += sum over blocks of partials[b][i]; one thread per counter, coalesced over i.

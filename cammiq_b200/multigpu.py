@@ -22,11 +22,14 @@ def combine_counters(counts, rcount_u=None, rcount_d=None, dst=0, group=None):
         return
     tensors = [counts] + [t for t in (rcount_u, rcount_d) if t is not None and t.numel() > 0]
     grouped = getattr(dist, "_coalescing_manager", None)
-    if counts.is_cuda and len(tensors) > 1 and grouped is not None:
-        # ONE grouped NCCL launch for the whole exchange (ncclGroupStart/End around the three sums);
-        # the coalescing manager groups all-reduces, which leaves the totals on rank `dst` as well
+    big = tensors[1:]
+    if counts.is_cuda and len(big) > 1 and grouped is not None and all(t.dtype == big[0].dtype for t in big):
+        # the two per-leaf arrays (same type) go out as ONE grouped NCCL launch (ncclGroupStart/End
+        # around the sums); the coalescing manager groups all-reduces of one type, which leaves the
+        # totals on rank `dst` as well.  The small counter block (another type) is its own reduce.
+        dist.reduce(counts, dst=dst, op=dist.ReduceOp.SUM, group=group)
         with grouped(group=group, device=counts.device):
-            for t in tensors:
+            for t in big:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return
     for t in tensors:
