@@ -401,6 +401,7 @@ extern "C" int cq_reset(cq_ctx *c) {
 	CQ_CUDA(cudaMemsetAsync(c->d_counts, 0, (ncnt + 4) * sizeof(unsigned long long), c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_u, 0, std::max<size_t>(c->n_leaves_u, 1) * 4, c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_d, 0, std::max<size_t>(c->n_leaves_d, 1) * 4, c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count + 7, 0, 8, c->stream)); // the pair records held
 	c->sc_reads_since_reset = 0;
 	return CQ_OK; // stream-ordered; every reader of the counters is on the same stream
 }
@@ -470,11 +471,22 @@ static int stageReads(cq_ctx *c, bool packed, const uint8_t *bases, const uint64
 	// byte range the reads span in the caller's buffer, and the longest read (sets the tile size)
 	uint64_t lo = ~0ull, hi = 0;
 	uint32_t max_len = 1;
-	for (uint64_t i = 0; i < n_reads; i++) {
-		uint64_t off = offsets ? offsets[i] : i * stride;
-		lo = std::min(lo, off);
-		hi = std::max(hi, off + (packed ? packedBytes(lengths[i]) : lengths[i]));
-		max_len = std::max<uint32_t>(max_len, lengths[i]);
+	if (offsets != NULL) {
+		for (uint64_t i = 0; i < n_reads; i++) {
+			lo = std::min(lo, offsets[i]);
+			hi = std::max(hi, offsets[i] + (packed ? packedBytes(lengths[i]) : lengths[i]));
+			max_len = std::max<uint32_t>(max_len, lengths[i]);
+		}
+	} else if (n_reads > 0) {
+		// fixed stride: the span starts at 0 and only the reads within 255 bytes of the end can set its extent
+		for (uint64_t i = 0; i < n_reads; i++)
+			max_len = std::max<uint32_t>(max_len, lengths[i]);
+		lo = 0;
+		for (uint64_t i = n_reads; i-- > 0;) {
+			hi = std::max(hi, i * stride + (packed ? packedBytes(lengths[i]) : lengths[i]));
+			if ((n_reads - 1 - i) * stride >= 255)
+				break;
+		}
 	}
 	if (hi < lo) lo = hi = 0;
 	const uint64_t copy_lo = lo & ~15ull, total = hi - copy_lo;
@@ -617,6 +629,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.rcount_u = c->d_rcount_u;
 	sp.rcount_d = c->d_rcount_d;
 	sp.pair_records = c->d_pairs;
+	sp.pair_count = c->d_probe_count + 7; // last word of the statistics block: survives the per-step clearing of the first five
 	sp.hit_spill = c->d_spill;
 	sp.dedup_sets = c->d_dedup;
 	sp.probe_count = c->d_probe_count;
@@ -738,7 +751,7 @@ static int beginStep(cq_ctx *c, cudaEvent_t **sev) {
 		}
 	}
 	*sev = c->steps[c->steps_used++].e;
-	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 64, c->stream));
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 40, c->stream));
 	return CQ_OK;
 }
 
@@ -779,7 +792,8 @@ int cqCollectPairs(cq_ctx *c, std::vector<cq_pair_count> &out) {
 	CQ_CUDA(cudaSetDevice(c->device));
 	const size_t ncnt = 2 * ((size_t) c->n_genomes + 1);
 	unsigned long long nrec = 0;
-	CQ_CUDA(cudaMemcpyAsync(&nrec, c->d_counts + ncnt + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+	(void) ncnt;
+	CQ_CUDA(cudaMemcpyAsync(&nrec, c->d_probe_count + 7, 8, cudaMemcpyDeviceToHost, c->stream));
 	CQ_CUDA(cudaStreamSynchronize(c->stream));
 	if (nrec == 0)
 		return CQ_OK;

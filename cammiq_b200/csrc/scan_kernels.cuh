@@ -91,9 +91,10 @@ struct ScanParams {
 	// outputs
 	int smem_counters;        // 1: block-private genome counters + partials, 0: global atomics
 	uint32_t *partials;       // [gridDim.x][2*(G+1)]
-	unsigned long long *counts; // [2*(G+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid n_pair_records
+	unsigned long long *counts; // [2*(G+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid (reserved)
 	uint32_t *rcount_u, *rcount_d;
 	unsigned long long *pair_records; // SC: (a<<32|b) per D_PAIR read
+	unsigned long long *pair_count;   // SC: records held (NOT in the counter block: callers sum that block across devices)
 	uint32_t *hit_spill;      // [total warps][32][spill_stride]
 	uint32_t spill_stride;    // per-read overflow capacity: 4*(longest - h + 1) - kHitSeg hits at most
 	uint32_t *dedup_sets;     // [total warps][dedup_slots] hash-set scratch of the cooperative dedup
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 			if (m) {
 				unsigned long long base = 0;
 				if (lane == __ffs(m) - 1)
-					base = atomicAdd(&p.counts[2 * G1 + 3], (unsigned long long) __popc(m));
+					base = atomicAdd(p.pair_count, (unsigned long long) __popc(m));
 				base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
 				if (inc_b)
 					p.pair_records[base + __popc(m & lt_mask)] = ((unsigned long long) rid_a << 32) | rid_b;

@@ -341,7 +341,8 @@ int cq_sync(cq_ctx *ctx);
 int cq_fetch(cq_ctx *ctx, int mode, cq_result *out);
 
 typedef struct {
-	void *d_counts;        /* uint64[2*(n_genomes+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid n_pair_records */
+	void *d_counts;        /* uint64[2*(n_genomes+1)+4]: cnt_u | cnt_d | nundet nconf n_invalid (reserved); summing this
+	                          block over devices gives the totals -- nothing device-local lives in it */
 	uint64_t n_counts;
 	void *d_rcount_u;      /* uint32[n_leaves_u] */
 	uint64_t n_rcount_u;

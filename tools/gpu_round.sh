@@ -17,6 +17,8 @@ cat $out/ab.jsonl
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
 ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2.csv python tools/kernel_ab.py --iters 1 > /dev/null 2>&1
 ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg3.csv python tools/kernel_ab.py --iters 1 --workload cfg3 > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2_random_reads.csv python tools/kernel_ab.py --iters 1 --random-reads > /dev/null 2>&1
+python tools/kernel_ab.py --random-reads >> $out/ab.jsonl 2>> $out/ab.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > $out/ncu_bench.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:scan_reads -c 1 -o $out/scan_full python tools/kernel_ab.py --iters 1 > $out/ncu_full.log 2>&1
 ls -la $out

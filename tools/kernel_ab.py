@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--packed", action="store_true")
     ap.add_argument("--mode", default="p")
     ap.add_argument("--iters", type=int, default=8)
+    ap.add_argument("--random-reads", action="store_true",
+                    help="uniform random reads unrelated to the genomes: (almost) no candidates, so the kernel's L2 traffic is "
+                         "the filter probes plus the tile words -- isolates the filter's L2 hit rate under ncu")
     ap.add_argument("--workdir", default=os.environ.get("CAMMIQ_BENCH_DIR", "/tmp"))
     a = ap.parse_args()
     w = dict(bench.WORKLOADS[a.workload])
@@ -40,7 +43,11 @@ def main():
         idx.set_filter_budget(int(a.filter_mb * (1 << 20)))
     ctx = cq.Context(0).upload(idx, w["n_genomes"])
     n, rl = w["reads"], w["read_len"]
-    reads = sl.make_reads(bench.synth_params(w), 0, n, rl, w["erate"])
+    if a.random_reads:
+        rng = np.random.default_rng(12345)
+        reads = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n, rl), dtype=np.uint8)]
+    else:
+        reads = sl.make_reads(bench.synth_params(w), 0, n, rl, w["erate"])
     lengths = np.full(n, rl, np.uint8)
     if a.packed:
         pk, pl, _ = cq.pack_reads(reads.reshape(-1), None, lengths, stride=rl, threads=8)
@@ -66,7 +73,7 @@ def main():
         chk += [int(r["rcount_u"].sum()), int(r["rcount_d"].sum()),
                 int((r["rcount_u"].astype(np.uint64) * (np.arange(len(r["rcount_u"]), dtype=np.uint64) % 1000003)).sum())]
     print(json.dumps({"lib": os.path.basename(cq.capi.library_path()), "workload": a.workload, "reads": n, "read_len": rl,
-                      "packed": a.packed, "filter_mb": idx.info.filter_bytes / (1 << 20),
+                      "packed": a.packed, "random_reads": a.random_reads, "filter_mb": idx.info.filter_bytes / (1 << 20),
                       "scan_ms_mean": float(np.mean(ms)), "scan_ms_min": float(np.min(ms)), "pack_ms_mean": float(np.mean(pk)),
                       "reads_per_s": n / (float(np.mean(ms)) * 1e-3),
                       "regs": t["regs_per_thread"], "grid": t["grid_blocks"], "blocks_per_sm": t["blocks_per_sm"],
