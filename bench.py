@@ -198,6 +198,29 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Several ranks share a host: keep a rank's threads (the host packer) and its page-locked buffers on the
+    NUMA node its GPU hangs off.  Best effort; returns a description for the config block."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = bdf[-12:] if len(bdf) > 12 else bdf            # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return "gpu %d: no NUMA node reported" % local
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if len(mine) < 2:
+            return "gpu %d on node %d: fewer than 2 of its cpus in this process's mask" % (local, node)
+        os.sched_setaffinity(0, mine)
+        return "gpu %d -> NUMA node %d, %d cpus" % (local, node, len(mine))
+    except Exception as e:
+        return "not bound (%s)" % str(e)[:80]
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -714,6 +737,8 @@ def run(json_fd):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback.")
     torch.cuda.set_device(local)
     host_group = None
+    ncpu_unbound = host_threads()
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("CAMMIQ_NO_NUMA_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         host_group = dist.new_group(backend="gloo")   # host-side waits that must not occupy the GPUs
@@ -917,7 +942,7 @@ def run(json_fd):
             sec = float(t.item())
         return sec, r, tmq
 
-    ncpu = host_threads()
+    ncpu = ncpu_unbound
     pack_threads = args.pack_threads if args.pack_threads >= 0 else min(16, ncpu // world)
     if pack_threads < 2 and args.pack_threads < 0:
         pack_threads = 0
@@ -1109,7 +1134,7 @@ def run(json_fd):
                        "l2_policy": "inputs larger than L2: %.2f GB prefix table + %.2f GB reads per step" % (
                            info.n_table_buckets * 32 / 1e9, n * rl / 1e9),
                        "parallelism": "index replicated, reads sharded, counters combined over NCCL once per step (counter block + one grouped launch for the two rcount arrays)" if world > 1 else "1 GPU",
-                       "index_prepare_s": t_index},
+                       "index_prepare_s": t_index, "numa": numa},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "d2h_note": "reduced totals, rank 0 only" if world > 1 else "totals",
                     "ms_per_step": e2e_s * 1e3, "path": e2e_path, "paths": e2e_paths},
