@@ -564,8 +564,9 @@ static int launchPack(cq_ctx *c, const ReadBatch &rb) {
 		CQ_CUDA(cudaMemcpyAsync(c->d_len2[s], rb.lengths, rb.n, cudaMemcpyDeviceToDevice, c->stream));
 		q.lengths_out = c->d_len2[s];
 	}
-	q.reads_per_block = 256 / q.words_per_read;
-	q.inv_words = (65536 + q.words_per_read - 1) / q.words_per_read;
+	q.base_words = (std::max<uint32_t>(rb.max_len, 1) + 15) / 16;
+	q.reads_per_block = 256 / q.base_words;
+	q.inv_words = (65536 + q.base_words - 1) / q.base_words;
 	q.n_passes = (q.n_padded + q.reads_per_block - 1) / q.reads_per_block;
 	const unsigned blocks = (unsigned) std::min<uint64_t>(q.n_passes, (uint64_t) c->n_sms * 16);
 	if (rb.packed)

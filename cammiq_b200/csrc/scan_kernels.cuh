@@ -904,8 +904,9 @@ struct PackParams {
 	const uint8_t *lengths_in;
 	uint64_t n_reads, n_padded; // n_padded = n_reads rounded up to 32
 	uint32_t words_per_read;
-	uint32_t reads_per_block;  // floor(256 / words_per_read)
-	uint32_t inv_words;        // ceil(2^16 / words_per_read)
+	uint32_t base_words;       // ceil(longest / 16): the words of a read that can hold bases
+	uint32_t reads_per_block;  // floor(256 / base_words)
+	uint32_t inv_words;        // ceil(2^16 / base_words)
 	uint64_t n_passes;         // ceil(n_padded / reads_per_block)
 	uint32_t *words;           // [n_padded][words_per_read]
 	uint8_t *lengths_out;      // ASCII input: a copy of lengths_in in which invalid reads are zeroed
@@ -919,12 +920,13 @@ __device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
 
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
-	// a block pass takes floor(256 / words_per_read) whole reads: read and word of a thread come from
-	// 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / words_per_read);
+	// a block pass takes floor(256 / base_words) whole reads, one thread per word that can hold bases
+	// (the slack words of a read are zeroed by the thread of its last word): read and word of a thread
+	// come from 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / base_words);
 	// the grid is persistent (a few blocks per SM striding over the passes): with one short-lived
 	// block per pass the launch of 350 000 blocks was what the kernel waited for
 	const uint32_t k = (threadIdx.x * q.inv_words) >> 16;
-	const uint32_t c = threadIdx.x - k * q.words_per_read;
+	const uint32_t c = threadIdx.x - k * q.base_words;
 	if (k >= q.reads_per_block)
 		return;
 	for (uint64_t pass = blockIdx.x; pass < q.n_passes; pass += gridDim.x) {
@@ -982,6 +984,9 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
 			}
 		}
 		q.words[idx] = word;
+		if (c + 1 == q.base_words)
+			for (uint32_t z = q.base_words; z < q.words_per_read; z++)
+				q.words[idx + 1 + (z - q.base_words)] = 0u;
 	}
 }
 
