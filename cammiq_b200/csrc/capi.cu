@@ -979,11 +979,12 @@ static int pipelineHostPack(cq_ctx *c, int mode, const uint8_t *bases, const uin
 	const AsciiReads in = {bases, offsets, stride, lengths};
 	const bool dense = offsets != NULL;
 	double pack_ms = 0;
-	// The packer is bound by the host's memory bandwidth, the ASCII path by PCIe: with a page-locked
-	// caller buffer every `direct_every`-th chunk crosses PCIe as it is (the copy engine moves it while
-	// the workers pack the next chunks), which shortens the step by the share the two resources allow
-	// (1 chunk in 8 on the hosts measured: 1.0 GB at ~47 GB/s against 1.0 GB packed in ~8.4 ms).
-	int direct_every = getenv("CAMMIQ_DIRECT_EVERY") ? atoi(getenv("CAMMIQ_DIRECT_EVERY")) : 8;
+	// The packer is bound by the host's memory bandwidth, the ASCII path by PCIe, so with a page-locked
+	// caller buffer some chunks could cross PCIe as they are while the workers pack the others
+	// (CAMMIQ_DIRECT_EVERY = n: every n-th chunk).  Measured with n = 8 at equal packer speed: 14.8 ms
+	// against 13.0 ms per 10M reads without -- the one 100 MB copy lengthens the pipeline's tail by
+	// more than it takes off the packers -- so the default is off.
+	int direct_every = getenv("CAMMIQ_DIRECT_EVERY") ? atoi(getenv("CAMMIQ_DIRECT_EVERY")) : 0;
 	if (direct_every > 0) {
 		cudaPointerAttributes attr;
 		if (cudaPointerGetAttributes(&attr, bases) != cudaSuccess || attr.type != cudaMemoryTypeHost) {

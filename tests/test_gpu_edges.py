@@ -1,6 +1,6 @@
 """Edge cases of the CUDA path against the oracle: extreme hash lengths, more genomes than the
-shared-memory counters hold (global-atomic path), sparse / non-monotonic read offsets (direct
-global loads instead of TMA-staged tiles), maximum read length, both tables empty, and the
+shared-memory counters hold (global-atomic path), sparse / non-monotonic read offsets (the pack
+kernel gathers every read from wherever it lies), maximum read length, both tables empty, and the
 size-independent properties of the scan at the benchmark's full size."""
 import os
 
@@ -130,8 +130,8 @@ def test_more_genomes_than_shared_counters(ctx, tmp_path):
 
 
 def test_sparse_and_shuffled_offsets_use_direct_loads(ctx, tmp_path):
-    """Reads scattered over a buffer with gaps and in shuffled order: the 32 reads of a
-    sub-tile span more than the staging buffer, so the kernel reads them from global memory."""
+    """Reads scattered over a buffer with gaps and in shuffled order, at every byte alignment:
+    the pack kernel assembles each 16-base word from the aligned words it touches."""
     rng = np.random.default_rng(9)
     seq = random_seq(rng, 5000)
     pu, pd = build_case(tmp_path, 18, 5, seq, stride=4, tag="sparse")
