@@ -567,8 +567,8 @@ static int launchPack(cq_ctx *c, const ReadBatch &rb) {
 	q.base_words = (std::max<uint32_t>(rb.max_len, 1) + 15) / 16;
 	q.reads_per_block = 256 / q.base_words;
 	q.inv_words = (65536 + q.base_words - 1) / q.base_words;
-	q.n_passes = (q.n_padded + q.reads_per_block - 1) / q.reads_per_block;
-	const unsigned blocks = (unsigned) std::min<uint64_t>(q.n_passes, (uint64_t) c->n_sms * 16);
+	const uint64_t n_passes = (q.n_padded + q.reads_per_block - 1) / q.reads_per_block;
+	const unsigned blocks = (unsigned) std::min<uint64_t>(n_passes, (uint64_t) c->n_sms * 16);
 	if (rb.packed)
 		pack_tiles_kernel<true><<<blocks, 256, 0, c->stream>>>(q);
 	else

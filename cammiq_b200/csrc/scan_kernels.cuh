@@ -2,27 +2,33 @@
 //
 //   pack_tiles_kernel      reads as the caller holds them (ASCII, or 2-bit bytes packed by the host)
 //                          -> the scan's tile layout: 16 bases per 32-bit word, first base in the
-//                          top bits, a fixed number of words per read.  ASCII is decoded and
-//                          validated here (A1).  Streaming, coalesced, HBM-bound.
+//                          top bits, a fixed (odd) number of words per read.  ASCII is decoded and
+//                          validated here (A1).  Streaming and coalesced; bound by instruction
+//                          issue, not by HBM.
 //   scan_reads_kernel      A2-A8 in one launch, persistent grid.  Every WARP owns tiles of 32
 //                          reads and runs four steps per tile, with no block-wide barrier:
 //                            stage    one TMA bulk copy (cp.async.bulk + mbarrier) brings the
-//                                     tile's words into one of the warp's two shared-memory
-//                                     buffers; the NEXT tile's copy is issued before this tile is
-//                                     scanned.  The kernel keeps its shared memory small on
-//                                     purpose: the in-flight probes live in the SM's L1, which is
-//                                     what is left of the 256 KB after the carve-out;
+//                                     tile's words into the warp's shared-memory buffer (one per
+//                                     warp; a second one that prefetches the next tile is a build
+//                                     option that measured slower).  The kernel keeps its shared
+//                                     memory small on purpose: the in-flight probes live in the
+//                                     SM's L1, which is what is left of the 256 KB after the
+//                                     carve-out the host sets explicitly;
 //                            phase 1  the tile's read positions are cut into strips of 8; a lane
 //                                     takes a strip, extracts its first h-mer from three packed
 //                                     words, rolls the hashes of BOTH strands through the strip
-//                                     in registers and issues all 8 probes (membership-filter
-//                                     words in L2, or the 16 key bytes of the table bucket when
-//                                     the index is too large for a filter) before testing any of
-//                                     them; positives are compacted into the warp's queue by
+//                                     in registers and issues the strip's probes (one membership-
+//                                     filter word in L2 per position; the 16 key bytes of the
+//                                     table bucket when the index has no filter; filter word AND
+//                                     bucket keys when the filter is only a sieve); the words of a
+//                                     half strip are tested while the next half strip's loads are
+//                                     in flight; positives are compacted into the warp's queue by
 //                                     ballot, no atomics;
 //                            phase 2  one queued candidate per lane: probe the prefix table in
-//                                     HBM (one 32-byte sector = one bucket), descend the CSR
-//                                     trie, append leaves to the owning read's hit list;
+//                                     HBM (one 32-byte sector = one bucket; the next bucket only
+//                                     if the home bucket is flagged overflowed), descend the
+//                                     path-compressed trie (a unary chain of up to 32 bases is one
+//                                     node), append leaves to the owning read's hit list;
 //                            phase 3  lane r: leaf set of read r -> decision -> counters.  Reads
 //                                     with long hit lists are deduplicated by the whole warp
 //                                     through a hash set; genome counters are combined across
@@ -50,7 +56,10 @@
 
 namespace cammiq {
 
-static const int kScanThreads = 256;          // 8 warps, each streaming its own 32-read tiles
+#ifndef CAMMIQ_SCAN_THREADS
+#define CAMMIQ_SCAN_THREADS 256
+#endif
+static const int kScanThreads = CAMMIQ_SCAN_THREADS; // 8 warps, each streaming its own 32-read tiles
 static const int kWarpsPerBlock = kScanThreads / 32;
 #ifndef CAMMIQ_STRIP
 #define CAMMIQ_STRIP 8
@@ -64,7 +73,7 @@ static const int kHitSeg = 4;                 // per-read hit slots in shared me
 static const int kTileBufs = CAMMIQ_TILE_BUFS; // 2: the next tile's copy overlaps the scan of this one
 static const int kLightHits = 16;             // longer hit lists are deduplicated by the whole warp
 static const int kProbeUnroll = 4;            // micro-benchmark unroll
-static const int kMaxBlocksPerSM = 4;
+static const int kMaxBlocksPerSM = CAMMIQ_MIN_BLOCKS > 4 ? CAMMIQ_MIN_BLOCKS : 4;
 static const uint32_t kMaxSmemGenomes = 1023; // 2*(G+1) u32 block counters stay below 8 KB of shared memory
 static const uint32_t kSetEmpty = 0xFFFFFFFFu;
 
@@ -907,10 +916,16 @@ struct PackParams {
 	uint32_t base_words;       // ceil(longest / 16): the words of a read that can hold bases
 	uint32_t reads_per_block;  // floor(256 / base_words)
 	uint32_t inv_words;        // ceil(2^16 / base_words)
-	uint64_t n_passes;         // ceil(n_padded / reads_per_block)
 	uint32_t *words;           // [n_padded][words_per_read]
 	uint8_t *lengths_out;      // ASCII input: a copy of lengths_in in which invalid reads are zeroed
 };
+
+// prmt without the selector masking __byte_perm adds (the callers' selector nibbles are 0..7 by construction)
+__device__ __forceinline__ uint32_t prmt(uint32_t x, uint32_t y, uint32_t sel) {
+	uint32_t v;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(x), "r"(y), "r"(sel));
+	return v;
+}
 
 __device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
 	uint32_t v;
@@ -921,72 +936,79 @@ __device__ __forceinline__ uint32_t ldgU32(const uint8_t *a) {
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256) pack_tiles_kernel(PackParams q) {
 	// a block pass takes floor(256 / base_words) whole reads, one thread per word that can hold bases
-	// (the slack words of a read are zeroed by the thread of its last word): read and word of a thread
-	// come from 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below 2^16 / base_words);
-	// the grid is persistent (a few blocks per SM striding over the passes): with one short-lived
-	// block per pass the launch of 350 000 blocks was what the kernel waited for
+	// (the two or three slack words of a read are zeroed by the thread of its last word): read and word
+	// of a thread come from 32-bit arithmetic with a precomputed reciprocal (exact for thread ids below
+	// 2^16 / base_words).  The grid is persistent (a few blocks per SM striding over the passes), and a
+	// thread keeps its word column: input and output addresses advance by constants.  The kernel is
+	// bound by the integer pipe (about 130 instructions per 16 bases; ncu: ALU 74 %, DRAM 41 %), not by HBM: everything below is written to
+	// keep that count down.
 	const uint32_t k = (threadIdx.x * q.inv_words) >> 16;
 	const uint32_t c = threadIdx.x - k * q.base_words;
 	if (k >= q.reads_per_block)
 		return;
-	for (uint64_t pass = blockIdx.x; pass < q.n_passes; pass += gridDim.x) {
-		const uint64_t r = pass * q.reads_per_block + k;
-		if (r >= q.n_padded)
-			break;
-		const uint64_t idx = r * q.words_per_read + c;
+	const bool last_word = c + 1 == q.base_words;
+	const bool slack3 = q.words_per_read - q.base_words == 3; // (base_words + 2) | 1: two or three slack words
+	const bool strided = !q.offsets && !(PACKED_IN && q.offsets32);
+	const uint64_t step = (uint64_t) gridDim.x * q.reads_per_block;
+	uint64_t r = (uint64_t) blockIdx.x * q.reads_per_block + k;
+	uint32_t *out = q.words + r * q.words_per_read + c;
+	const uint64_t out_step = step * q.words_per_read;
+	const uint32_t col = (PACKED_IN ? 4u : 16u) * c; // byte of this thread's word within a read
+	const uint8_t *in = q.bases + (q.read_base + r) * q.stride + col;
+	const uint64_t in_step = step * q.stride;
+	const int first_base = (int) (16u * c);
+	for (; r < q.n_padded; r += step, out += out_step, in += in_step) {
 		uint32_t word = 0;
-		if (r < q.n_reads) {
-			const int n = (int) q.lengths_in[r] - (int) (16u * c); // bases of this read in word c
-			if (n > 0) {
-				unsigned long long off;
-				if (PACKED_IN)
-					off = q.offsets32 ? (unsigned long long) q.offsets32[r] : q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
-				else
-					off = q.offsets ? q.offsets[r] : (q.read_base + r) * q.stride;
-				if (PACKED_IN) {
-					// four bytes of the host-packed read = this word, big-endian; bytes past the read are masked
-					const uint8_t *a = q.bases + off + 4u * c;
-					const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
-					const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
-					const uint32_t w0 = ldgU32(al), w1 = sh ? ldgU32(al + 4) : 0u; // an aligned word never needs the next one
-					word = __byte_perm(__funnelshift_r(w0, w1, sh), 0u, 0x0123);
-				} else {
-					// sixteen ASCII bytes at any alignment: five aligned words, funnel-shifted
-					const uint8_t *a = q.bases + off + 16u * c;
-					const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
-					const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
-					const uint32_t nw = ((uint32_t) ((uintptr_t) a & 3u) + (uint32_t) min(n, 16) + 3u) >> 2; // aligned words the bases touch
-					uint32_t w[5];
+		const int n = r < q.n_reads ? (int) q.lengths_in[r] - first_base : 0; // bases of this read in word c
+		if (n > 0) {
+			const uint8_t *a = in;
+			if (!strided)
+				a = q.bases + col + (PACKED_IN && q.offsets32 ? (uint64_t) q.offsets32[r] : q.offsets[r]);
+			const uint8_t *al = (const uint8_t *) ((uintptr_t) a & ~(uintptr_t) 3);
+			const uint32_t sh = (uint32_t) ((uintptr_t) a & 3u) * 8u;
+			const uint32_t n16 = (uint32_t) min(n, 16);
+			if (PACKED_IN) {
+				// four bytes of the host-packed read = this word, big-endian; bytes past the read are masked
+				const uint32_t w0 = ldgU32(al), w1 = sh ? ldgU32(al + 4) : 0u; // an aligned word never needs the next one
+				word = __byte_perm(__funnelshift_r(w0, w1, sh), 0u, 0x0123);
+			} else {
+				// sixteen ASCII bytes at any alignment: up to five aligned words, funnel-shifted
+				const uint32_t nw = ((sh >> 3) + n16 + 3u) >> 2; // aligned words the bases touch
+				uint32_t w[5];
 #pragma unroll
-					for (int t = 0; t < 5; t++)
-						w[t] = (uint32_t) t < nw ? ldgU32(al + 4 * t) : 0u;
-					uint32_t bad = 0;
+				for (int t = 0; t < 5; t++)
+					w[t] = (uint32_t) t < nw ? ldgU32(al + 4 * t) : 0u;
+				uint32_t bad = 0, g[4];
 #pragma unroll
-					for (int t = 0; t < 4; t++) {
-						const uint32_t d = __funnelshift_r(w[t], w[t + 1], sh);
-						// codes A/a=0 C/c=1 G/g=2 T/t=3 in each byte; validity: fold case and compare with the
-						// letter each code stands for (one byte permute)
-						const uint32_t t4 = (d >> 1) & 0x03030303u;
-						const uint32_t code4 = t4 ^ ((t4 >> 1) & 0x01010101u);
-						const uint32_t nib = code4 | (code4 >> 4);
-						const uint32_t expect4 = __byte_perm(0x54474341u, 0u, (nib & 0xFFu) | ((nib >> 8) & 0xFF00u));
-						const int left = n - 4 * t;
-						const uint32_t live = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
-						bad |= ((d & 0xDFDFDFDFu) ^ expect4) & live;
-						// four 2-bit codes -> one byte, first base in the top bits
-						word |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * t);
-					}
-					if (bad)
-						q.lengths_out[r] = 0; // every thread of an invalid read that sees a bad byte stores the same 0
+				for (int t = 0; t < 4; t++) {
+					const uint32_t d = __funnelshift_r(w[t], w[t + 1], sh);
+					// codes A/a=0 C/c=1 G/g=2 T/t=3 from bits 1 and 2 of each byte (on anything else the code is
+					// arbitrary and the comparison below fails); validity: fold case and compare with the letter
+					// each code stands for (the four codes gathered into one permute selector)
+					const uint32_t code4 = ((d >> 1) ^ (d >> 2)) & 0x03030303u;
+					const uint32_t nib = code4 | (code4 >> 4);
+					const uint32_t expect4 = prmt(0x54474341u, 0u, prmt(nib, 0u, 0x0020u));
+					// bytes past the read do not count: all-ones shifted left by 8 x (bases left), the shift
+					// clamped to [0, 32], marks them
+					const int left = 8 * (int) n16 - 32 * t;
+					const uint32_t dead = __funnelshift_lc(0u, 0xFFFFFFFFu, (uint32_t) (t == 0 ? left : max(left, 0)));
+					bad |= ((d & 0xDFDFDFDFu) ^ expect4) & ~dead;
+					// four 2-bit codes -> the top byte, first base in the top bits
+					g[t] = code4 * 0x40100401u;
 				}
-				if (n < 16)
-					word &= 0xFFFFFFFFu << (32 - 2 * n);
+				if (bad)
+					q.lengths_out[r] = 0; // every thread of an invalid read that sees a bad byte stores the same 0
+				word = prmt(prmt(g[3], g[2], 0x0073u), prmt(g[1], g[0], 0x7300u), 0x7610u);
 			}
+			word &= __funnelshift_lc(0u, 0xFFFFFFFFu, 32u - 2u * n16);
 		}
-		q.words[idx] = word;
-		if (c + 1 == q.base_words)
-			for (uint32_t z = q.base_words; z < q.words_per_read; z++)
-				q.words[idx + 1 + (z - q.base_words)] = 0u;
+		out[0] = word;
+		if (last_word) {
+			out[1] = 0u;
+			out[2] = 0u;
+			if (slack3)
+				out[3] = 0u;
+		}
 	}
 }
 

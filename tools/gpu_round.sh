@@ -1,11 +1,21 @@
 #!/bin/bash
-# One GPU-box session of a finished build: GPU tests, both bench arms, ncu evidence (launch list of the bench
-# command, metrics and full capture of the scan kernel).  Everything lands in gpurun_out/<tag>/.
+# One GPU-box session of a finished build: GPU tests, ncu figures of the scan kernel (stamped into
+# profiles/scan_traffic.json BEFORE the bench reads them), both bench arms, the launch list of the bench
+# command and one full capture of the scan kernel.  Everything lands in gpurun_out/<tag>/.
 tag=${1:-round}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/gputests.log 2>&1
 echo "tests rc=$?"; tail -3 $out/gputests.log
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
+ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2.csv python tools/kernel_ab.py --iters 1 > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg3.csv python tools/kernel_ab.py --iters 1 --workload cfg3 > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2_random_reads.csv python tools/kernel_ab.py --iters 1 --random-reads > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:pack_tiles -c 1 --csv --log-file $out/ncu_metrics_pack.csv python tools/kernel_ab.py --iters 1 > /dev/null 2>&1
+python tools/ncu_to_traffic.py $out/ncu_metrics_cfg2.csv cfg2 profiles/r02_scan_ncu_metrics_cfg2.csv > $out/stamp.log 2>&1
+python tools/ncu_to_traffic.py $out/ncu_metrics_cfg3.csv cfg3 profiles/r02_scan_ncu_metrics_cfg3.csv >> $out/stamp.log 2>&1
+python tools/ncu_to_traffic.py $out/ncu_metrics_cfg2_random_reads.csv cfg2_random_reads profiles/r02_scan_ncu_metrics_cfg2_random_reads.csv >> $out/stamp.log 2>&1
+cp profiles/scan_traffic.json $out/scan_traffic.json
 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_reference.json 2> $out/bench_reference.err
 echo "reference rc=$?"
 python bench.py > $out/bench.json 2> $out/bench.err
@@ -13,12 +23,10 @@ echo "bench rc=$?"; tail -c 600 $out/bench.err
 python tools/kernel_ab.py > $out/ab.jsonl 2> $out/ab.err
 python tools/kernel_ab.py --mode sc >> $out/ab.jsonl 2>> $out/ab.err
 python tools/kernel_ab.py --workload cfg3 >> $out/ab.jsonl 2>> $out/ab.err
-cat $out/ab.jsonl
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
-ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2.csv python tools/kernel_ab.py --iters 1 > /dev/null 2>&1
-ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg3.csv python tools/kernel_ab.py --iters 1 --workload cfg3 > /dev/null 2>&1
-ncu --metrics $M --clock-control none -k regex:scan_reads -c 1 --csv --log-file $out/ncu_metrics_cfg2_random_reads.csv python tools/kernel_ab.py --iters 1 --random-reads > /dev/null 2>&1
 python tools/kernel_ab.py --random-reads >> $out/ab.jsonl 2>> $out/ab.err
+cat $out/ab.jsonl
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > $out/ncu_bench.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:scan_reads -c 1 -o $out/scan_full python tools/kernel_ab.py --iters 1 > $out/ncu_full.log 2>&1
+ncu -i $out/scan_full.ncu-rep --page details > $out/scan_ncu_details.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; echo "smoke rc=$?"
 ls -la $out
