@@ -769,11 +769,27 @@ def run(json_fd):
     log("[bench] rank %d: index %d U + %d D leaves, table %.2f GB, %d reads ready (%.1f s)" % (
         rank, info.n_leaves_u, info.n_leaves_d, info.n_table_buckets * 32 / 1e9, n, time.time() - t0))
 
-    counts, rc_u, rc_d = (torch.as_tensor(a, device="cuda") for a in ctx.device_counter_arrays())
+    def as_tensors(arrays):
+        return tuple(torch.as_tensor(a, device="cuda") for a in arrays)
+
+    # the context's two accumulator sets (cq_swap_accumulators): with several ranks the NCCL reduce of one
+    # step's counters runs on a side stream while the next step packs and scans into the other set
+    overlap = world > 1 and mode == cq.MODE_P and not os.environ.get("CAMMIQ_NO_REDUCE_OVERLAP")
+    acc_sets = [as_tensors(ctx.device_counter_arrays())]
+    if overlap:
+        ctx.swap_accumulators()
+        acc_sets.append(as_tensors(ctx.device_counter_arrays()))
+        ctx.swap_accumulators()
+    cur = [0]                                    # index of the set the context accumulates into
+    main_stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream() if overlap else None
+    ev_scanned = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_reduced = [None, None]
 
     def combine():
         # the one collective of the path: sum the counter block (and the per-leaf rcount in
         # mode P) into rank 0 over NCCL, one grouped launch
+        counts, rc_u, rc_d = acc_sets[cur[0]]
         if mode == cq.MODE_P:
             multigpu.combine_counters(counts, rc_u, rc_d)
         else:
@@ -788,9 +804,33 @@ def run(json_fd):
     ctx.stage(reads.reshape(-1), None, lengths, stride=rl)
 
     def step_resident():
+        if overlap and mode == cq.MODE_P:
+            # step k: [wait until the reduce that last read this set is done] reset, pack, scan on the
+            # context's stream; then the set is handed to the side stream, which reduces it while step
+            # k+1 runs on the other set.  Every step is still reduced in full.
+            k = cur[0]
+            if ev_reduced[k] is not None:
+                main_stream.wait_event(ev_reduced[k])
+            ctx.reset()
+            ctx.query_staged(mode)
+            ev_scanned[k].record(main_stream)
+            ctx.swap_accumulators()
+            with torch.cuda.stream(side_stream):
+                side_stream.wait_event(ev_scanned[k])
+                multigpu.combine_counters(*acc_sets[k])
+                if ev_reduced[k] is None:
+                    ev_reduced[k] = torch.cuda.Event()
+                ev_reduced[k].record(side_stream)
+            cur[0] = k ^ 1
+            return
         ctx.reset()
         ctx.query_staged(mode)
         combine()
+
+    def join_reduces():
+        # the timed region ends when the last step's reduce has: the context's stream waits for the side stream
+        if overlap:
+            main_stream.wait_stream(side_stream)
 
     for _ in range(args.warmup):
         step_resident()
@@ -805,6 +845,7 @@ def run(json_fd):
     e0.record()
     for _ in range(args.steps):
         step_resident()
+    join_reduces()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -1079,6 +1120,7 @@ def run(json_fd):
             a0.record()
             for _ in range(k3):
                 step_resident()
+            join_reduces()
             a1.record()
             barrier()
             t = torch.tensor([a0.elapsed_time(a1)], device="cuda", dtype=torch.float64)
@@ -1133,7 +1175,8 @@ def run(json_fd):
                        "filter_mb": info.filter_bytes / (1 << 20),
                        "l2_policy": "inputs larger than L2: %.2f GB prefix table + %.2f GB reads per step" % (
                            info.n_table_buckets * 32 / 1e9, n * rl / 1e9),
-                       "parallelism": "index replicated, reads sharded, counters combined over NCCL once per step (counter block + one grouped launch for the two rcount arrays)" if world > 1 else "1 GPU",
+                       "parallelism": ("index replicated, reads sharded, counters combined over NCCL once per step (counter block + one grouped launch for the two rcount arrays)"
+                                       + ("; the reduce of step k runs on a side stream while step k+1 scans into the context's other accumulator set (cq_swap_accumulators)" if overlap else "")) if world > 1 else "1 GPU",
                        "index_prepare_s": t_index, "numa": numa},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "d2h_note": "reduced totals, rank 0 only" if world > 1 else "totals",

@@ -132,6 +132,7 @@ SYMBOLS = {
     "cq_sync": (C.c_int, [C.c_void_p]),
     "cq_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "cq_get_device_counters": (C.c_int, [C.c_void_p, C.POINTER(DeviceCounters)]),
+    "cq_swap_accumulators": (C.c_int, [C.c_void_p, C.POINTER(DeviceCounters)]),
     "cq_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cq_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "cq_timing_reset": (C.c_int, [C.c_void_p]),
@@ -239,6 +240,7 @@ class _CudaArray:
     """Zero-copy view of a device buffer through __cuda_array_interface__ (for torch.as_tensor)."""
 
     def __init__(self, ptr, n, typestr):
+        self.ptr = int(ptr or 0)
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr,
                                          "data": (int(ptr), False), "version": 2, "strides": None}
 
@@ -411,6 +413,15 @@ class Context:
         """(counts as int64 view, rcount_u, rcount_d as int32 views) exposing
         __cuda_array_interface__; integer sums are bit-identical in two's complement."""
         dc = self.device_counters()
+        return (_CudaArray(dc.d_counts, dc.n_counts, "<i8"),
+                _CudaArray(dc.d_rcount_u, max(dc.n_rcount_u, 1), "<i4"),
+                _CudaArray(dc.d_rcount_d, max(dc.n_rcount_d, 1), "<i4"))
+
+    def swap_accumulators(self):
+        """Make the context's other accumulator set current (cq_swap_accumulators); returns the arrays of
+        the set that was current, as device_counter_arrays() does."""
+        dc = DeviceCounters()
+        _check(lib().cq_swap_accumulators(self._h, C.byref(dc)))
         return (_CudaArray(dc.d_counts, dc.n_counts, "<i8"),
                 _CudaArray(dc.d_rcount_u, max(dc.n_rcount_u, 1), "<i4"),
                 _CudaArray(dc.d_rcount_d, max(dc.n_rcount_d, 1), "<i4"))

@@ -168,6 +168,8 @@ static void freeDevice(cq_ctx *c) {
 	cudaFree(c->d_table); cudaFree(c->d_nodes_u); cudaFree(c->d_nodes_d);
 	cudaFree(c->d_leaf_u_ref); cudaFree(c->d_leaf_d_ref); cudaFree(c->d_counts);
 	cudaFree(c->d_rcount_u); cudaFree(c->d_rcount_d); cudaFree(c->d_partials);
+	cudaFree(c->d_counts_alt); cudaFree(c->d_rcount_u_alt); cudaFree(c->d_rcount_d_alt);
+	c->d_counts_alt = NULL; c->d_rcount_u_alt = c->d_rcount_d_alt = NULL;
 	cudaFree(c->d_spill); cudaFree(c->d_dedup); cudaFree(c->d_probe_count); cudaFree(c->d_filter);
 	c->d_filter = NULL;
 	c->d_dedup = NULL;
@@ -1239,6 +1241,34 @@ extern "C" int cq_get_device_counters(cq_ctx *c, cq_device_counters *out) {
 	out->n_rcount_u = c->n_leaves_u;
 	out->d_rcount_d = c->d_rcount_d;
 	out->n_rcount_d = c->n_leaves_d;
+	return CQ_OK;
+}
+
+extern "C" int cq_swap_accumulators(cq_ctx *c, cq_device_counters *previous) {
+	if (c == NULL || !c->has_index)
+		return fail(CQ_ESTATE, "cq_swap_accumulators: no index resident.");
+	CQ_CUDA(cudaSetDevice(c->device));
+	const size_t n_counts = 2 * ((size_t) c->n_genomes + 1) + 4;
+	if (c->d_counts_alt == NULL) {
+		const size_t nu = std::max<size_t>(c->n_leaves_u, 1), nd = std::max<size_t>(c->n_leaves_d, 1);
+		CQ_CUDA(cudaMalloc((void **) &c->d_counts_alt, n_counts * sizeof(unsigned long long)));
+		CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u_alt, nu * 4));
+		CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d_alt, nd * 4));
+		CQ_CUDA(cudaMemsetAsync(c->d_counts_alt, 0, n_counts * sizeof(unsigned long long), c->stream));
+		CQ_CUDA(cudaMemsetAsync(c->d_rcount_u_alt, 0, nu * 4, c->stream));
+		CQ_CUDA(cudaMemsetAsync(c->d_rcount_d_alt, 0, nd * 4, c->stream));
+	}
+	if (previous) {
+		previous->d_counts = c->d_counts;
+		previous->n_counts = n_counts;
+		previous->d_rcount_u = c->d_rcount_u;
+		previous->n_rcount_u = c->n_leaves_u;
+		previous->d_rcount_d = c->d_rcount_d;
+		previous->n_rcount_d = c->n_leaves_d;
+	}
+	std::swap(c->d_counts, c->d_counts_alt);
+	std::swap(c->d_rcount_u, c->d_rcount_u_alt);
+	std::swap(c->d_rcount_d, c->d_rcount_d_alt);
 	return CQ_OK;
 }
 

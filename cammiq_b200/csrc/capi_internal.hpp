@@ -54,6 +54,9 @@ struct cq_ctx {
 	// accumulators
 	unsigned long long *d_counts = NULL; // 2*(G+1)+4
 	uint32_t *d_rcount_u = NULL, *d_rcount_d = NULL;
+	// the other accumulator set of cq_swap_accumulators (NULL until its first call)
+	unsigned long long *d_counts_alt = NULL;
+	uint32_t *d_rcount_u_alt = NULL, *d_rcount_d_alt = NULL;
 	uint32_t *d_partials = NULL;
 	uint32_t *d_spill = NULL; // per-read hit overflow, [max grid warps][32][spill_stride]; grows with the longest read seen
 	uint32_t *d_dedup = NULL; // hash-set scratch of the cooperative leaf dedup, [max grid warps][dedup_slots]

@@ -350,6 +350,15 @@ typedef struct {
 	uint64_t n_rcount_d;
 } cq_device_counters;
 int cq_get_device_counters(cq_ctx *ctx, cq_device_counters *out);
+/* Double-buffered accumulators, for a caller that overlaps ITS reduction of one batch's counters (the
+ * collective of SURVEY.md section 8e) with the scan of the next batch.  The context owns two accumulator
+ * sets (counter block + both rcount arrays; the second is allocated and zeroed at the first call).  The
+ * call makes the other set current -- everything enqueued afterwards (cq_reset, scans, cq_fetch,
+ * cq_get_device_counters) uses it -- and reports the set that WAS current in *previous (may be NULL).
+ * Host-side pointer exchange only: work already enqueued keeps the set it was launched with.  The
+ * caller orders its reads of `previous` after the context's stream (an event) and finishes them before
+ * it swaps back and writes that set again. */
+int cq_swap_accumulators(cq_ctx *ctx, cq_device_counters *previous);
 /* The cudaStream_t every call of this context enqueues on (for the caller's collectives). */
 int cq_get_stream(cq_ctx *ctx, void **stream);
 

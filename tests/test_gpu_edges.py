@@ -155,6 +155,43 @@ def test_sparse_and_shuffled_offsets_use_direct_loads(ctx, tmp_path):
     compare(ctx, pu, pd, 5, None, bases=b2, offsets=off2, lengths=len2)
 
 
+def test_two_accumulator_sets(ctx, tmp_path):
+    """cq_swap_accumulators: two batches scanned into the two sets stay apart (each set holds exactly its
+    own batch, counters and per-leaf rcount), resets touch only the current set, and the arrays the swap
+    reports are those of the set that was current."""
+    rng = np.random.default_rng(31)
+    seq = random_seq(rng, 5000)
+    G = 6
+    pu, pd = build_case(tmp_path, 18, G, seq, stride=3, tag="swap")
+    oi_u, oi_d = ol.OracleIndex(pu), ol.OracleIndex(pd)
+    batches = [sample_reads(rng, seq, 500, 50, 150, err=0.01), sample_reads(rng, seq, 300, 40, 200, err=0.0)]
+    packed = [ol.pack_reads(b) for b in batches]
+    want = [ol.oracle_query(oi_u, oi_d, ol.MODE_P, G, *pk) for pk in packed]
+    assert not np.array_equal(want[0]["rcount_u"], want[1]["rcount_u"])
+    ctx.upload(cq.Index(pu, pd), G)
+
+    def check(got, w):
+        for k in ("cnt_u", "cnt_d", "rcount_u", "rcount_d"):
+            assert np.array_equal(got[k], w[k]), k
+        assert (int(got["nundet"]), int(got["nconf"])) == (w["nundet"], w["nconf"])
+
+    first = ctx.device_counters()
+    check(ctx.query(cq.MODE_P, *packed[0]), want[0])            # set A <- batch 0
+    prev = ctx.swap_accumulators()                                # B current (fresh: zeroed)
+    assert prev[1].ptr == first.d_rcount_u and ctx.device_counters().d_rcount_u != first.d_rcount_u
+    check(ctx.query(cq.MODE_P, *packed[1]), want[1])            # set B <- batch 1 only
+    ctx.swap_accumulators()                                       # A current again, untouched by batch 1
+    assert ctx.device_counters().d_rcount_u == first.d_rcount_u
+    check(ctx.fetch(cq.MODE_P), want[0])
+    ctx.reset()                                                   # zeroes A, not B
+    ctx.swap_accumulators()
+    check(ctx.fetch(cq.MODE_P), want[1])
+    ctx.reset()
+    ctx.swap_accumulators()
+    got = ctx.fetch(cq.MODE_P)
+    assert int(got["rcount_u"].sum()) == 0 and int(got["cnt_u"].sum()) == 0
+
+
 def test_empty_index_pair(ctx, tmp_path):
     for name, first in (("e.bin1", 0x40), ("e.bin2", 0xC0)):
         (tmp_path / name).write_bytes(b"\xff" * 10)
