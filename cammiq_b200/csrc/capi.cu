@@ -373,6 +373,7 @@ extern "C" int cq_index_upload(cq_ctx *c, const cq_index *idx, uint32_t n_genome
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_u, std::max<size_t>(c->n_leaves_u, 1) * 4));
 	CQ_CUDA(cudaMalloc((void **) &c->d_rcount_d, std::max<size_t>(c->n_leaves_d, 1) * 4));
 	CQ_CUDA(cudaMalloc((void **) &c->d_probe_count, 8 * sizeof(unsigned long long)));
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count, 0, 8 * sizeof(unsigned long long), c->stream));
 
 	if (!f.filter.empty()) {
 		if ((rc = uploadArray((uint64_t **) &c->d_filter, f.filter.data(), f.filter.size(), up)) != 0) return rc;
@@ -403,7 +404,7 @@ extern "C" int cq_reset(cq_ctx *c) {
 	CQ_CUDA(cudaMemsetAsync(c->d_counts, 0, (ncnt + 4) * sizeof(unsigned long long), c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_u, 0, std::max<size_t>(c->n_leaves_u, 1) * 4, c->stream));
 	CQ_CUDA(cudaMemsetAsync(c->d_rcount_d, 0, std::max<size_t>(c->n_leaves_d, 1) * 4, c->stream));
-	CQ_CUDA(cudaMemsetAsync(c->d_probe_count + 7, 0, 8, c->stream)); // the pair records held
+	CQ_CUDA(cudaMemsetAsync(c->d_probe_count + 6, 0, 16, c->stream)); // the scan's tile counter, the pair records held
 	c->sc_reads_since_reset = 0;
 	return CQ_OK; // stream-ordered; every reader of the counters is on the same stream
 }
@@ -636,6 +637,7 @@ static int launchScan(cq_ctx *c, int mode, const ReadBatch &rb) {
 	sp.hit_spill = c->d_spill;
 	sp.dedup_sets = c->d_dedup;
 	sp.probe_count = c->d_probe_count;
+	sp.tile_counter = reinterpret_cast<uint32_t *>(c->d_probe_count + 6); // 0 between launches (the kernel resets it)
 	if (c->want_per_read) {
 		sp.read_class = c->d_read_class + rb.first;
 		sp.read_rid_a = c->d_read_rid_a + rb.first;

@@ -109,6 +109,7 @@ struct ScanParams {
 	uint32_t *dedup_sets;     // [total warps][dedup_slots] hash-set scratch of the cooperative dedup
 	uint32_t dedup_slots;     // power of two >= 2 * (kHitSeg + spill_stride)
 	uint32_t light_hits;      // hit lists up to this length are deduplicated by their lane (kLightHits)
+	uint32_t *tile_counter;   // dynamic tile hand-out: 0 at launch, reset by the warp that takes the last tile
 	unsigned long long *probe_count; // [5]: probes, candidates, leaf hits, chained bucket loads, bucket-key loads behind the sieve
 	// optional per-read outputs
 	uint8_t *read_class;
@@ -448,7 +449,23 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 
 	if (sub < n_sub && kTileBufs == 2)
 		issueCopy(sub, 0);
+#if !defined(CAMMIQ_STATIC_TILES) && CAMMIQ_TILE_BUFS == 1
+	// Tiles are handed out dynamically: a warp's first tile is its own index, every further one comes
+	// from a global counter (tile = number of warps + the counter's old value), fetched at the START of
+	// the tile in work so that the atomic's round trip hides behind the tile.  A CTA that becomes
+	// resident late (a collective or another stream's kernel holds its slot for a while) then simply
+	// takes fewer tiles instead of finishing its fixed share late.  Every processed tile takes exactly
+	// one number, so the n_sub-th taker is the last one of the launch and leaves the counter at 0.
+	uint32_t taken = 0;
+	for (uint32_t it = 0; sub < n_sub; it++) {
+		if (lane == 0) {
+			taken = atomicAdd(p.tile_counter, 1u);
+			if (taken == n_sub - 1)
+				atomicExch(p.tile_counter, 0u);
+		}
+#else
 	for (uint32_t it = 0; sub < n_sub; sub += warp_stride, it++) {
+#endif
 		const uint32_t buf = kTileBufs == 2 ? (it & 1u) : 0u;
 		// the other buffer is free (its tile was finished one iteration ago): the next tile's words
 		// arrive while this tile is scanned
@@ -862,6 +879,12 @@ __global__ void __launch_bounds__(kScanThreads, CAMMIQ_MIN_BLOCKS) scan_reads_ke
 			}
 		}
 		__syncwarp(); // every lane is done with the packed tile and the warp state
+#if !defined(CAMMIQ_STATIC_TILES) && CAMMIQ_TILE_BUFS == 1
+		{
+			const unsigned long long nx = (unsigned long long) warp_stride + __shfl_sync(0xffffffffu, taken, 0);
+			sub = nx < n_sub ? (uint32_t) nx : n_sub;
+		}
+#endif
 	}
 
 	// ---- block totals ---------------------------------------------------------------------------------
