@@ -832,14 +832,33 @@ def run(json_fd):
         if overlap:
             main_stream.wait_stream(side_stream)
 
+    # nvidia-smi needs a few hundred ms to come up and samples every 100 ms; the timed region is a few
+    # tens of ms.  The sampler therefore runs while the SAME steps keep the GPU under load: untimed steps
+    # until its first sample has arrived, the timed steps, untimed steps until three samples are in.
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def keep_loaded(want_samples, max_s):
+        t_start = time.time()
+        while True:
+            for _ in range(20):
+                step_resident()
+            join_reduces()
+            torch.cuda.synchronize()
+            more = rank == 0 and len(sampler.rows) < want_samples and time.time() - t_start < max_s
+            if world > 1:   # rank 0 decides for everyone: the steps contain collectives
+                f = torch.tensor([1 if more else 0], device="cuda")
+                dist.all_reduce(f, op=dist.ReduceOp.MAX)
+                more = bool(f.item())
+            if not more:
+                return
+
     for _ in range(args.warmup):
         step_resident()
+    keep_loaded(1, 4.0)
     barrier()
     ctx.timing_reset()
     launches0 = ctx.timing()["kernel_launches"]
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -850,8 +869,10 @@ def run(json_fd):
     barrier()
     ms_total = e0.elapsed_time(e1)
     tm = ctx.timing()
-    clocks = sampler.stop()
     launches = tm["kernel_launches"] - launches0
+    keep_loaded(3, 2.0)
+    clocks = sampler.stop()
+    clocks["note"] = "sampled every 100 ms while untimed copies of the step ran before and after the %d timed steps" % args.steps
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
