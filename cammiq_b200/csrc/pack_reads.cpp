@@ -152,7 +152,77 @@ static const size_t kPrefetchAhead = prefetchAhead();
 	}
 CAMMIQ_SLICE_LOOP(sliceScalar, , packScalar)
 #ifdef CAMMIQ_X86
-CAMMIQ_SLICE_LOOP(sliceAvx512, __attribute__((target("avx512f,avx512bw,avx512vl"))), packAvx512)
+// Reads of one length L (a multiple of 4) that lie back to back (stride == L, packed stride == L/4) are
+// ONE stream of bases: 16 reads = L/4 whole 64-byte blocks, converted without a mask, a tail or a per-read
+// loop; the bytes land exactly where the per-read path would put them.  Returns false when a byte outside
+// ACGTacgt was met (the caller then repeats these 16 reads one by one to find the invalid ones).
+template <bool NT>
+__attribute__((target("avx512f,avx512bw,avx512vl"))) inline bool packStream16(const uint8_t *s, uint32_t n_bytes, uint8_t *dst,
+		size_t prefetch_ahead) {
+	const __m512i three = _mm512_set1_epi8(3), fold = _mm512_set1_epi8((char) 0xDF);
+	const __m512i letters = _mm512_broadcast_i32x4(_mm_setr_epi8('A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+	const __m512i pair = _mm512_set1_epi16(0x0104), quad = _mm512_set1_epi32(0x00010010);
+	__mmask64 bad = 0;
+	for (uint32_t j = 0; j < n_bytes; j += 64) {
+		CAMMIQ_PREFETCH(s + j + prefetch_ahead);
+		const __m512i w = _mm512_loadu_si512(reinterpret_cast<const void *>(s + j));
+		// code = bits 1 and 2 of the letter, Gray-decoded: ((w >> 1) ^ (w >> 2)) & 3 (the 16-bit shifts leak
+		// a neighbour's bits only into bits 6-7, which the mask drops)
+		const __m512i code = _mm512_ternarylogic_epi32(_mm512_srli_epi16(w, 1), _mm512_srli_epi16(w, 2), three, 0x28);
+		bad |= _mm512_cmpneq_epi8_mask(_mm512_and_si512(w, fold), _mm512_shuffle_epi8(letters, code));
+		const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(code, pair), quad);
+		// the packed bytes are read next by the DMA engine, not by this core: with a 16-byte aligned
+		// destination they bypass the cache (no read-for-ownership of the output lines)
+		if (NT)
+			_mm_stream_si128(reinterpret_cast<__m128i *>(dst + (j >> 2)), _mm512_cvtepi32_epi8(p32));
+		else
+			_mm_storeu_si128(reinterpret_cast<__m128i *>(dst + (j >> 2)), _mm512_cvtepi32_epi8(p32));
+	}
+	return bad == 0;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl"))) uint64_t sliceAvx512(const SliceArgs &x) {
+	uint64_t bad = 0, at = x.at;
+	const uint64_t L = x.in->stride;
+	const bool stream = !x.dense && x.in->offsets == NULL && L >= 4 && L <= 255 && (L & 3) == 0 && x.stride == L / 4;
+	const __m128i want = _mm_set1_epi8((char) L);
+	bool streamed = false;
+	for (uint64_t k = x.a; k < x.b;) {
+		uint64_t upto = k + 1;
+		if (stream && k + 16 <= x.b &&
+			_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(x.in->lengths + x.first + k)), want)) == 0xFFFF) {
+			const uint8_t *src = x.in->bases + (x.first + k) * L;
+			uint8_t *dst = x.out + k * x.stride;
+			const bool ok = ((uintptr_t) dst & 15) == 0 ? packStream16<true>(src, (uint32_t) (16 * L), dst, kPrefetchAhead)
+													   : packStream16<false>(src, (uint32_t) (16 * L), dst, kPrefetchAhead);
+			if (ok) {
+				_mm_storeu_si128(reinterpret_cast<__m128i *>(x.out_lengths + k), want);
+				streamed = true;
+				k += 16;
+				continue;
+			}
+			upto = k + 16; // an invalid byte among these 16 reads: one by one
+		}
+		for (; k < upto; k++) {
+			const uint64_t i = x.first + k;
+			const uint32_t len = x.in->lengths[i];
+			const uint8_t *src = x.in->bases + (x.in->offsets ? x.in->offsets[i] : i * x.in->stride);
+			uint8_t *dst = x.out + (x.dense ? at : k * x.stride);
+			CAMMIQ_PREFETCH(src + kPrefetchAhead);
+			CAMMIQ_PREFETCH(src + kPrefetchAhead + 64);
+			const bool ok = packAvx512(src, len, dst);
+			x.out_lengths[k] = ok ? (uint8_t) len : 0;
+			bad += ok ? 0 : 1;
+			if (x.dense) {
+				x.out_offsets[k] = (uint32_t) at;
+				at += packedBytes(len);
+			}
+		}
+	}
+	if (streamed)
+		_mm_sfence(); // the streaming stores are visible before the worker reports its slice done
+	return bad;
+}
 CAMMIQ_SLICE_LOOP(sliceAvx2, __attribute__((target("avx2"))), packAvx2)
 #endif
 

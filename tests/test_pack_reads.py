@@ -84,6 +84,41 @@ def test_every_length_and_tail_padding_is_zero():
         assert not packed[i, len(want):].any(), i
 
 
+@pytest.mark.parametrize("L", [4, 100, 152, 252])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_back_to_back_reads_of_one_length(L, threads):
+    """Reads of one length (a multiple of 4) lying back to back take the packer's streaming path (16 reads =
+    whole 64-byte blocks); invalid bytes, lower case, a read of another length in the middle and a count that
+    is not a multiple of 16 must give exactly what the per-read path gives."""
+    rng = np.random.default_rng(1000 + L + threads)
+    n = 16 * 23 + 7
+    bases = rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), n * L).astype(np.uint8)
+    lengths = np.full(n, L, dtype=np.uint8)
+    bad_reads = {0, 15, 16, 77, 200, 201, n - 1, n - 8}
+    for i in sorted(bad_reads):
+        bases[i * L + int(rng.integers(0, L))] = rng.choice(np.frombuffer(b"NnXR-*@\x00\xff", dtype=np.uint8))
+    bases[5 * L - 1] = ord("N") if L > 4 else bases[5 * L - 1]      # last base of read 4
+    if L > 4:
+        bad_reads.add(4)
+    short = {40: L - 1, 41: 0, 130: L - 4}                            # other lengths inside the stream
+    for i, ln in short.items():
+        lengths[i] = ln
+    packed, out_len, bad = cq.pack_reads(bases, None, lengths, stride=L, threads=threads)
+    assert packed.shape[1] == L // 4
+    n_bad = 0
+    for i in range(n):
+        ln = int(lengths[i])
+        read = bases[i * L:i * L + ln].tobytes()
+        want, valid = numpy_pack(read)
+        if valid:
+            assert out_len[i] == ln, i
+            assert np.array_equal(packed[i, :len(want)], want), i
+        else:
+            assert out_len[i] == 0, i
+            n_bad += 1
+    assert bad == n_bad and n_bad >= len(bad_reads) - 3
+
+
 def test_stride_too_small_is_rejected():
     with pytest.raises(cq.CammiqError):
         cq.pack_reads(np.frombuffer(b"ACGTACGTA", dtype=np.uint8), None, np.array([9], np.uint8), stride=9,
