@@ -128,6 +128,8 @@ static size_t prefetchAhead() {
 	return e ? (size_t) atol(e) : 4096;
 }
 static const size_t kPrefetchAhead = prefetchAhead();
+// CAMMIQ_PACK_STREAM=0 (experiments): back-to-back reads of one length go through the per-read loop too
+static const bool kStreamPath = !(getenv("CAMMIQ_PACK_STREAM") && atoi(getenv("CAMMIQ_PACK_STREAM")) == 0);
 
 // the loop is stamped out per ISA so that the packer inlines into it
 #define CAMMIQ_SLICE_LOOP(NAME, TARGET, PACK)                                                     \
@@ -184,7 +186,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) inline bool packStream16(co
 __attribute__((target("avx512f,avx512bw,avx512vl"))) uint64_t sliceAvx512(const SliceArgs &x) {
 	uint64_t bad = 0, at = x.at;
 	const uint64_t L = x.in->stride;
-	const bool stream = !x.dense && x.in->offsets == NULL && L >= 4 && L <= 255 && (L & 3) == 0 && x.stride == L / 4;
+	const bool stream = kStreamPath && !x.dense && x.in->offsets == NULL && L >= 4 && L <= 255 && (L & 3) == 0 && x.stride == L / 4;
 	const __m128i want = _mm_set1_epi8((char) L);
 	bool streamed = false;
 	for (uint64_t k = x.a; k < x.b;) {
