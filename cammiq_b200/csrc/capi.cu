@@ -893,7 +893,13 @@ static int fetchPerRead(cq_ctx *c, uint64_t n, cq_result *out) {
 	return CQ_OK;
 }
 
-static const uint64_t kChunkReads = 1u << 20; // reads per pipeline stage of cq_query
+// reads per pipeline stage of cq_query (CAMMIQ_CHUNK_READS: experiments; rounded to whole tiles of 64 reads)
+static uint64_t chunkReads() {
+	const char *e = getenv("CAMMIQ_CHUNK_READS");
+	const uint64_t v = e ? (uint64_t) atoll(e) : 0;
+	return v >= (1u << 12) ? std::min<uint64_t>((v + 63) & ~63ull, 1u << 24) : (1u << 20);
+}
+static const uint64_t kChunkReads = chunkReads();
 
 template <typename T>
 static int ensureHost(T **ptr, size_t *cap, size_t need) {
