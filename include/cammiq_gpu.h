@@ -357,7 +357,8 @@ int cq_get_device_counters(cq_ctx *ctx, cq_device_counters *out);
  * cq_get_device_counters) uses it -- and reports the set that WAS current in *previous (may be NULL).
  * Host-side pointer exchange only: work already enqueued keeps the set it was launched with.  The
  * caller orders its reads of `previous` after the context's stream (an event) and finishes them before
- * it swaps back and writes that set again. */
+ * it swaps back and writes that set again.  The pair records of mode SC are not part of a set (they are
+ * gathered per call, not reduced): swap in mode P, or fetch the pairs before swapping. */
 int cq_swap_accumulators(cq_ctx *ctx, cq_device_counters *previous);
 /* The cudaStream_t every call of this context enqueues on (for the caller's collectives). */
 int cq_get_stream(cq_ctx *ctx, void **stream);
